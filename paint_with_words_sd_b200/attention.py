@@ -1,0 +1,259 @@
+"""The drop-in boundary: `inj_forward`, the replacement for diffusers' `CrossAttention.__call__`.
+
+Same calling convention, context-dict schema and patch mechanism as the reference
+(paint_with_words/paint_with_words.py:60-125 `inj_forward`, 193-195 / 556-559 patch sites):
+
+    inj_forward(self, hidden_states, context=None, mask=None) -> Tensor[B, N, C]
+    context: None (self-attention) | Tensor[B,77,Dc] | dict with
+        "CONTEXT_TENSOR", "CROSS_ATTENTION_WEIGHT_{N}" ([N,77] fp32 or int 0),
+        "CROSS_ATTENTION_WEIGHT_ORIG" ([H,W,77] fp32 or int 0), "SIGMA", "WEIGHT_FUNCTION"
+        (optional, ours) "WMAP_INDEX", "G_SIGMA"
+
+Everything between the q/k/v projections and the output projection runs in libpww_b200.so through
+the C ABI (include/pww_b200.h): one stats launch (per-image max/std of QK^T over all heads) and one
+fused launch (bias + softmax + PV).  No score tensor, head permute or mask broadcast is materialised.
+There is no PyTorch/CPU fallback for the cross-attention path: unsupported shapes or weight functions
+raise.
+
+Extensions beyond the reference (which is hard-wired to batch 1, paint_with_words.py:445):
+  * B > 1 with per-image statistics -- each image's max/std is its own, so results do not depend on
+    how images are batched or sharded across GPUs;
+  * dict key "WMAP_INDEX" (int32 [B] device tensor): image b uses weight map `WMAP_INDEX[b]` of a
+    stacked [Bw,N,77] map, -1 = no bias.  This is what lets the cond and uncond halves of
+    classifier-free guidance run as ONE batch-2 forward instead of two (paint_with_words.py:483-499).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import _native
+from .conditioning import expand_orig_weight_map, weight_key
+from .weight_function import g_of_sigma, probe_weight_function
+
+_ORIG_KEY = "CROSS_ATTENTION_WEIGHT_ORIG"
+
+
+class _DeviceState:
+    """Per-device scratch owned by the shim: G(sigma) device scalar, stats [B], stats workspace."""
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.g_sigma = torch.zeros(1, dtype=torch.float32, device=device)
+        self._g_key = None
+        self.stats = torch.zeros(64, dtype=torch.float32, device=device)
+        self.workspace = torch.zeros(1 << 20, dtype=torch.uint8, device=device)
+        self.index_cache: Dict[int, torch.Tensor] = {}
+
+    def set_g(self, key, value: float) -> None:
+        if key != self._g_key:
+            self.g_sigma.fill_(value)      # async fill on the current stream; no host sync
+            self._g_key = key
+
+    def ensure(self, batch: int, ws_bytes: int) -> None:
+        if self.stats.numel() < batch:
+            self.stats = torch.zeros(batch, dtype=torch.float32, device=self.device)
+        if self.workspace.numel() < ws_bytes:
+            self.workspace = torch.zeros(ws_bytes, dtype=torch.uint8, device=self.device)
+
+    def shared_index(self, batch: int) -> torch.Tensor:
+        t = self.index_cache.get(batch)
+        if t is None:
+            t = torch.zeros(batch, dtype=torch.int32, device=self.device)
+            self.index_cache[batch] = t
+        return t
+
+
+_STATES: Dict[torch.device, _DeviceState] = {}
+
+
+def _state(device: torch.device) -> _DeviceState:
+    s = _STATES.get(device)
+    if s is None:
+        s = _STATES[device] = _DeviceState(device)
+    return s
+
+
+def reset_device_state() -> None:
+    _STATES.clear()
+
+
+def resolve_weight_map(context: dict, n: int, device):
+    """`CROSS_ATTENTION_WEIGHT_{n}` lookup with the reference's ORIG fallback (paint_with_words.py:93-103),
+    expanded once per n and cached in the dict instead of re-interpolated at every call."""
+    try:
+        return context[weight_key(n)]
+    except KeyError:
+        w = context[_ORIG_KEY]
+        if isinstance(w, int):
+            return 0
+        w = expand_orig_weight_map(w.detach().to("cpu", torch.float32), n).to(device)
+        context[weight_key(n)] = w
+        return w
+
+
+def _rows(t: torch.Tensor) -> torch.Tensor:
+    """[B,L,C] fp16 with unit channel stride and 16-byte friendly strides."""
+    if t.dtype != torch.float16:
+        t = t.to(torch.float16)
+    if t.stride(-1) != 1 or (t.stride(0) % 8) or (t.stride(1) % 8) or (t.data_ptr() % 16):
+        t = t.contiguous()
+    return t
+
+
+def cross_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: float,
+                    wmap: Optional[torch.Tensor] = None, wmap_index: Optional[torch.Tensor] = None,
+                    stat: int = _native.PWW_STAT_MAX, g_sigma: Optional[torch.Tensor] = None,
+                    return_stats: bool = False):
+    """Fused region for a key sequence of <=128 tokens.  q [B,N,C]; k,v [B,T,C]; wmap [Bw,N,T] fp32 or None.
+    `g_sigma` is a 1-element fp32 device tensor holding G(sigma)."""
+    L = _native.lib()
+    q, k, v = _rows(q), _rows(k), _rows(v)
+    B, N, C = q.shape
+    T = k.shape[1]
+    D = C // heads
+    if k.stride() != v.stride():
+        v = v.contiguous()
+        k = k.contiguous()
+    out = torch.empty((B, N, C), dtype=torch.float16, device=q.device)
+    st = _state(q.device)
+    stream = torch.cuda.current_stream(q.device).cuda_stream
+    stats_ptr = g_ptr = w_ptr = idx_ptr = None
+    w_bs = 0
+    if wmap is not None:
+        if wmap.dtype != torch.float32 or not wmap.is_contiguous():
+            wmap = wmap.to(torch.float32).contiguous()
+        if wmap.dim() == 2:
+            wmap = wmap.unsqueeze(0)
+        if wmap.shape[1] != N or wmap.shape[2] != T:
+            raise ValueError(f"weight map shape {tuple(wmap.shape)} does not match N={N}, T={T}")
+        if wmap_index is None:
+            wmap_index = st.shared_index(B) if wmap.shape[0] == 1 else torch.arange(B, dtype=torch.int32, device=q.device)
+        ws_bytes = L.pww_xattn_workspace_bytes(B, heads, N, T, D)
+        st.ensure(B, ws_bytes)
+        rc = L.pww_xattn_stats_f16(q.data_ptr(), k.data_ptr(), B, heads, N, T, D, q.stride(0), q.stride(1),
+                                   k.stride(0), k.stride(1), stat, wmap_index.data_ptr(), st.stats.data_ptr(),
+                                   st.workspace.data_ptr(), st.workspace.numel(), stream)
+        _native.check(rc, "pww_xattn_stats_f16")
+        _native.launch_count += 1
+        stats_ptr, g_ptr = st.stats.data_ptr(), g_sigma.data_ptr()
+        w_ptr, idx_ptr, w_bs = wmap.data_ptr(), wmap_index.data_ptr(), wmap.stride(0)
+    rc = L.pww_xattn_fwd_f16(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, heads, N, T, D,
+                             q.stride(0), q.stride(1), k.stride(0), k.stride(1), out.stride(0), out.stride(1),
+                             w_ptr, w_bs, idx_ptr, stats_ptr, g_ptr, float(scale), stream)
+    _native.check(rc, "pww_xattn_fwd_f16")
+    _native.launch_count += 1
+    if return_stats:
+        return out, (st.stats[:B].clone() if wmap is not None else None)
+    return out
+
+
+# Self-attention: the native flash kernel when libpww_b200 provides it for the shape; until then the
+# library attention of torch is the declared stand-in.  bench.py records
+# which one ran in `config.self_attn`.
+SELF_ATTN_IMPL = "torch-sdpa"
+
+
+def self_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: float) -> torch.Tensor:
+    B, N, C = q.shape
+    D = C // heads
+    if SELF_ATTN_IMPL == "native":
+        L = _native.lib()
+        q, k, v = _rows(q), _rows(k), _rows(v)
+        if not (q.stride() == k.stride() == v.stride()):
+            q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        out = torch.empty((B, N, C), dtype=torch.float16, device=q.device)
+        rc = L.pww_attn_fwd_f16(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, heads, N, D,
+                                q.stride(0), q.stride(1), out.stride(0), out.stride(1), float(scale),
+                                torch.cuda.current_stream(q.device).cuda_stream)
+        _native.check(rc, "pww_attn_fwd_f16")
+        _native.launch_count += 1
+        return out
+    qh = q.reshape(B, N, heads, D).transpose(1, 2)
+    kh = k.reshape(B, k.shape[1], heads, D).transpose(1, 2)
+    vh = v.reshape(B, v.shape[1], heads, D).transpose(1, 2)
+    o = F.scaled_dot_product_attention(qh, kh, vh, scale=scale)
+    return o.transpose(1, 2).reshape(B, N, C)
+
+
+def inj_forward(self, hidden_states, context=None, mask=None):
+    """Replacement for `CrossAttention.__call__` (reference: paint_with_words.py:60-125)."""
+    if not hidden_states.is_cuda:
+        raise _native.NativeError("paint_with_words_sd_b200 attention runs on a B200 GPU only (no CPU path)")
+    is_dict = isinstance(context, dict)
+    if context is None:
+        ctx = hidden_states
+    else:
+        ctx = context["CONTEXT_TENSOR"] if is_dict else context
+
+    with torch.autocast("cuda", dtype=torch.float16):
+        q = self.to_q(hidden_states)
+        k = self.to_k(ctx)
+        v = self.to_v(ctx)
+
+    if context is None:
+        o = self_attention(q, k, v, self.heads, self.scale)
+    else:
+        wmap = wmap_index = g_dev = None
+        stat = _native.PWW_STAT_MAX
+        if is_dict:
+            f = context["WEIGHT_FUNCTION"]
+            sigma = context["SIGMA"]
+            w = resolve_weight_map(context, q.shape[1], q.device)
+            probed = probe_weight_function(f, sigma)
+            if isinstance(w, torch.Tensor) and not probed.is_zero:
+                g_dev = context.get("G_SIGMA")      # device scalar kept by PwWSampler (graph replay safe)
+                if g_dev is None:
+                    st = _state(q.device)
+                    st.set_g((id(f), float(sigma)), g_of_sigma(f, probed, sigma))
+                    g_dev = st.g_sigma
+                wmap, stat = w, probed.stat
+                wmap_index = context.get("WMAP_INDEX")
+        if k.shape[0] != q.shape[0]:
+            k = k.expand(q.shape[0], -1, -1)
+            v = v.expand(q.shape[0], -1, -1)
+        o = cross_attention(q, k, v, self.heads, self.scale, wmap, wmap_index, stat, g_dev)
+
+    with torch.autocast("cuda", dtype=torch.float16):
+        o = self.to_out[0](o)
+        o = self.to_out[1](o)
+    return o
+
+
+class PwWAttnProcessor:
+    """diffusers>=0.12 `AttnProcessor`-style hook: `attn.set_processor(PwWAttnProcessor())`; the PwW context
+    dict is passed as `encoder_hidden_states` exactly as with the class patch."""
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, **kwargs):
+        return inj_forward(attn, hidden_states, encoder_hidden_states, attention_mask)
+
+
+_PATCHED: Dict[type, object] = {}
+
+
+def patch_unet(unet, forward=inj_forward) -> int:
+    """Class-level `__call__` patch of every module whose class is named "CrossAttention"
+    (paint_with_words.py:193-195).  Returns the number of attention modules found."""
+    count = 0
+    for m in unet.modules():
+        if m.__class__.__name__ == "CrossAttention":
+            cls = m.__class__
+            if cls not in _PATCHED:
+                _PATCHED[cls] = cls.__dict__.get("__call__")
+            cls.__call__ = forward
+            count += 1
+    return count
+
+
+def unpatch_all() -> None:
+    """Undo `patch_unet` (the reference never undoes its patch; tests need to)."""
+    for cls, orig in _PATCHED.items():
+        if orig is None:
+            if "__call__" in cls.__dict__:
+                delattr(cls, "__call__")
+        else:
+            cls.__call__ = orig
+    _PATCHED.clear()

@@ -1,0 +1,164 @@
+// extern "C" entry points of libpww_b200.so (declared in include/pww_b200.h).
+#include <stdio.h>
+#include <string.h>
+
+#include "pww_common.cuh"
+#include "xattn_simt.cuh"
+
+namespace {
+
+thread_local char g_last_cuda_error[256] = "";
+
+int cuda_fail(cudaError_t e) {
+  snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+  return PWW_ERR_CUDA;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+bool supported_head_dim(int D) { return D == 40 || D == 64 || D == 80 || D == 160; }
+
+int check_common(const void* q, const void* k, int B, int H, int N, int T, int D, int64_t q_bs, int64_t q_rs,
+                 int64_t k_bs, int64_t k_rs) {
+  if (!q || !k || B <= 0 || H <= 0 || N <= 0 || T <= 0 || D <= 0) return PWW_ERR_BAD_ARG;
+  if (!aligned16(q) || !aligned16(k)) return PWW_ERR_BAD_ARG;
+  if ((q_bs | q_rs | k_bs | k_rs) & 7) return PWW_ERR_BAD_ARG;  // 16-byte vector access on rows
+  if (q_rs < (int64_t)H * D || k_rs < (int64_t)H * D) return PWW_ERR_BAD_ARG;
+  if (!supported_head_dim(D) || T > 128) return PWW_ERR_UNSUPPORTED;
+  return PWW_OK;
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int stats_ctas_per_image(int H, int N) { return H * pww::ceil_div(N, pww::simt::kRows); }
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return cuda_fail(e);
+  }
+  return PWW_OK;
+}
+
+template <int D>
+int launch_stats(const pww::XattnParams& p, cudaStream_t s) {
+  size_t smem = pww::simt::stats_smem(p.T, D);
+  int rc = set_smem(pww::simt::xattn_stats_kernel<D>, smem);
+  if (rc) return rc;
+  dim3 grid(pww::ceil_div(p.N, pww::simt::kRows), p.H, p.B);
+  pww::simt::xattn_stats_kernel<D><<<grid, pww::simt::kRows, smem, s>>>(p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? PWW_OK : cuda_fail(e);
+}
+
+template <int D>
+int launch_fwd(const pww::XattnParams& p, cudaStream_t s) {
+  size_t smem = pww::simt::fwd_smem(p.T, D);
+  int rc = set_smem(pww::simt::xattn_fwd_kernel<D>, smem);
+  if (rc) return rc;
+  dim3 grid(pww::ceil_div(p.N, pww::simt::kRows), p.H, p.B);
+  pww::simt::xattn_fwd_kernel<D><<<grid, pww::simt::kRows, smem, s>>>(p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? PWW_OK : cuda_fail(e);
+}
+
+}  // namespace
+
+extern "C" {
+
+int pww_version(void) { return 100; }  // 0.1.0
+
+const char* pww_status_str(int status) {
+  switch (status) {
+    case PWW_OK: return "ok";
+    case PWW_ERR_BAD_ARG: return "bad argument (null/misaligned pointer, non-positive size or stride not a multiple of 8)";
+    case PWW_ERR_UNSUPPORTED: return "unsupported shape (head dim must be 40/64/80/160, T <= 128)";
+    case PWW_ERR_CUDA: return "CUDA error (see pww_last_cuda_error)";
+    case PWW_ERR_WORKSPACE: return "workspace too small (see pww_xattn_workspace_bytes)";
+    default: return "unknown status";
+  }
+}
+
+const char* pww_last_cuda_error(void) { return g_last_cuda_error; }
+
+int pww_device_supported(void) {
+  int dev = 0, major = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e);
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return cuda_fail(e);
+  return major == 10 ? 1 : 0;
+}
+
+size_t pww_xattn_workspace_bytes(int B, int H, int N, int T, int D) {
+  (void)T; (void)D;
+  if (B <= 0 || H <= 0 || N <= 0) return 0;
+  return align_up((size_t)B * sizeof(unsigned int), 256) +
+         (size_t)B * stats_ctas_per_image(H, N) * sizeof(pww::StatPartial);
+}
+
+int pww_xattn_stats_f16(const void* q, const void* k, int B, int H, int N, int T, int D, int64_t q_batch_stride,
+                        int64_t q_row_stride, int64_t k_batch_stride, int64_t k_row_stride, int stat,
+                        const int32_t* wmap_index, float* stats, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  int rc = check_common(q, k, B, H, N, T, D, q_batch_stride, q_row_stride, k_batch_stride, k_row_stride);
+  if (rc) return rc;
+  if (!stats || !workspace || (stat != PWW_STAT_MAX && stat != PWW_STAT_STD)) return PWW_ERR_BAD_ARG;
+  if (workspace_bytes < pww_xattn_workspace_bytes(B, H, N, T, D)) return PWW_ERR_WORKSPACE;
+  pww::XattnParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = (const __half*)q; p.k = (const __half*)k;
+  p.B = B; p.H = H; p.N = N; p.T = T; p.D = D;
+  p.q_bs = q_batch_stride; p.q_rs = q_row_stride; p.k_bs = k_batch_stride; p.k_rs = k_row_stride;
+  p.wmap_index = wmap_index; p.stat = stat; p.stats_out = stats;
+  p.counters = (unsigned int*)workspace;
+  p.partials = (pww::StatPartial*)((char*)workspace + align_up((size_t)B * sizeof(unsigned int), 256));
+  p.ctas_per_image = stats_ctas_per_image(H, N);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (D) {
+    case 40: return launch_stats<40>(p, s);
+    case 64: return launch_stats<64>(p, s);
+    case 80: return launch_stats<80>(p, s);
+    case 160: return launch_stats<160>(p, s);
+  }
+  return PWW_ERR_UNSUPPORTED;
+}
+
+int pww_xattn_fwd_f16(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int T, int D,
+                      int64_t q_batch_stride, int64_t q_row_stride, int64_t k_batch_stride, int64_t k_row_stride,
+                      int64_t o_batch_stride, int64_t o_row_stride, const float* wmap, int64_t wmap_batch_stride,
+                      const int32_t* wmap_index, const float* stats, const float* g_sigma, float scale,
+                      void* stream) {
+  int rc = check_common(q, k, B, H, N, T, D, q_batch_stride, q_row_stride, k_batch_stride, k_row_stride);
+  if (rc) return rc;
+  if (!v || !out || !aligned16(v) || !aligned16(out)) return PWW_ERR_BAD_ARG;
+  if ((o_batch_stride | o_row_stride) & 7 || o_row_stride < (int64_t)H * D) return PWW_ERR_BAD_ARG;
+  if (wmap && (!stats || !g_sigma)) return PWW_ERR_BAD_ARG;
+  pww::XattnParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = (const __half*)q; p.k = (const __half*)k; p.v = (const __half*)v; p.out = (__half*)out;
+  p.B = B; p.H = H; p.N = N; p.T = T; p.D = D;
+  p.q_bs = q_batch_stride; p.q_rs = q_row_stride; p.k_bs = k_batch_stride; p.k_rs = k_row_stride;
+  p.o_bs = o_batch_stride; p.o_rs = o_row_stride;
+  p.wmap = wmap; p.wmap_bs = wmap_batch_stride; p.wmap_index = wmap_index;
+  p.stats = stats; p.g_sigma = g_sigma; p.scale = scale;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (D) {
+    case 40: return launch_fwd<40>(p, s);
+    case 64: return launch_fwd<64>(p, s);
+    case 80: return launch_fwd<80>(p, s);
+    case 160: return launch_fwd<160>(p, s);
+  }
+  return PWW_ERR_UNSUPPORTED;
+}
+
+int pww_attn_fwd_f16(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int D,
+                     int64_t qkv_batch_stride, int64_t qkv_row_stride, int64_t o_batch_stride, int64_t o_row_stride,
+                     float scale, void* stream) {
+  (void)q; (void)k; (void)v; (void)out; (void)B; (void)H; (void)N; (void)D; (void)qkv_batch_stride;
+  (void)qkv_row_stride; (void)o_batch_stride; (void)o_row_stride; (void)scale; (void)stream;
+  return PWW_ERR_UNSUPPORTED;  // tcgen05 flash kernel lands in attn_tc.cuh
+}
+
+}  // extern "C"
