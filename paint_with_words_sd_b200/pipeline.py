@@ -134,6 +134,7 @@ class PwWSampler:
         self.extra_input = extra_input            # inpaint: [m,5,h,w] (mask + masked-image latents)
         self.use_graph = use_graph and latents.is_cuda
         self._graph = None
+        self.native_launches_per_step = None
         self._probed = probe_weight_function(weight_function, 1.0)
         self._ctx = self._merge_contexts(cond_ctxs, uncond_ctxs)
         dev = self.device
@@ -202,6 +203,32 @@ class PwWSampler:
         self._params.copy_(self._table[i])
         self._ctx["SIGMA"] = self.scheduler.sigmas[step_index]
 
+    # -- host-buffer interface (what bench.py's e2e leg drives) -----------------------------------
+    def device_inputs(self) -> Dict[str, torch.Tensor]:
+        """Persistent device tensors a step reads: latents, the text context and the stacked weight maps.
+        Copying new values INTO them (same addresses) is valid between graph replays."""
+        d = {"latents": self.latents, "CONTEXT_TENSOR": self._ctx["CONTEXT_TENSOR"]}
+        for k, v in self._ctx.items():
+            if k.startswith("CROSS_ATTENTION_WEIGHT_") and isinstance(v, torch.Tensor) and v.is_cuda:
+                d[k] = v
+        return d
+
+    def stage_from_host(self, pinned: Dict[str, torch.Tensor]) -> int:
+        """Async H2D copy of this step's inputs from pinned host buffers; returns bytes copied."""
+        dev = self.device_inputs()
+        n = 0
+        for k, h in pinned.items():
+            dev[k].copy_(h, non_blocking=True)
+            n += h.numel() * h.element_size()
+        return n
+
+    def restart(self, latents: Optional[torch.Tensor] = None):
+        """Rewind to step 0 (fresh LMS history), optionally with new latents."""
+        self._step_no = 0
+        self._derivs.zero_()
+        if latents is not None:
+            self.latents.copy_(latents)
+
     def step(self):
         i = self._step_no
         step_index = self.scheduler.step_index_of(self.timesteps[i])
@@ -226,8 +253,11 @@ class PwWSampler:
         torch.cuda.current_stream(self.device).wait_stream(s)
         self.latents.copy_(snap[0]); self._derivs.copy_(snap[1])
         g = torch.cuda.CUDAGraph()
+        from . import _native
+        before = _native.launch_count
         with torch.cuda.graph(g):
             self._step_body()
+        self.native_launches_per_step = _native.launch_count - before
         self.latents.copy_(snap[0]); self._derivs.copy_(snap[1])
         self._graph = g
 

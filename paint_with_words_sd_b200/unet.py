@@ -54,8 +54,9 @@ class UNetConfig:
 
     @staticmethod
     def tiny(in_channels: int = 4) -> "UNetConfig":
-        """Same topology, 1/10 width: for CPU tests and the smoke run."""
-        return UNetConfig(in_channels=in_channels, block_out_channels=(32, 64, 128, 128), cross_attention_dim=64,
+        """Same topology at half width with 4 heads (head dims 40/80/160/160 -- inside the kernel family):
+        for CPU tests and the smoke run."""
+        return UNetConfig(in_channels=in_channels, block_out_channels=(160, 320, 640, 640), cross_attention_dim=64,
                           attention_heads=4, norm_num_groups=8, sample_size=16)
 
 

@@ -1,0 +1,162 @@
+"""GPU parity of the CUDA path (through the C ABI) against the oracle on identical seeded inputs.
+
+Tolerances (frozen here):
+  * statistic scalar: relative 2^-10 (one fp16 ulp) against the oracle's fp16-emulating form;
+  * attention output vs the fp32 oracle:            max|d| <= 2e-3 * max|out|  (fp16 storage of Q/K/V/P/O);
+  * attention output vs the fp16-emulating oracle:  max|d| <= 1e-3 * max|out|.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pww_oracle as O
+from paint_with_words_sd_b200 import _native
+from paint_with_words_sd_b200 import attention as A
+
+pytestmark = pytest.mark.gpu
+
+SD15_512 = [(4096, 8, 40), (1024, 8, 80), (256, 8, 160), (64, 8, 160)]
+SD15_256 = [(16, 8, 160)]
+SD21_768 = [(9216, 5, 64), (2304, 10, 64), (576, 20, 64), (144, 20, 64)]
+RAGGED = [(100, 8, 40), (1, 2, 64), (129, 3, 80), (333, 1, 160)]
+
+
+def _inputs(B, N, H, D, T, seed):
+    g = torch.Generator().manual_seed(seed)
+    C = H * D
+    q = (torch.randn(B, N, C, generator=g) * 0.5).half()
+    k = (torch.randn(B, T, C, generator=g) * 0.5).half()
+    v = (torch.randn(B, T, C, generator=g) * 0.5).half()
+    w = torch.zeros(B, N, T)
+    for b in range(B):                      # sparse columns like the real maps, plus overlap
+        cols = torch.randperm(T, generator=g)[:9]
+        for c in cols:
+            w[b, :, c] += (torch.rand(N, generator=g) > 0.6).float() * float(torch.rand(1, generator=g) * 2)
+    return q, k, v, w
+
+
+def _oracle(q, k, v, H, scale, w, g, stat, emulate):
+    outs, stats = [], []
+    for b in range(q.shape[0]):
+        box = {}
+
+        def bias_fn(s, b=b):
+            m = s.max() if stat == "max" else s.std()
+            box["m"] = float(m)
+            return g * w[b] * m.float() if w is not None else 0.0
+        outs.append(O.attention_core(q[b:b + 1].float(), k[b:b + 1].float(), v[b:b + 1].float(), H, scale,
+                                     bias_fn if w is not None else None, emulate_fp16=emulate))
+        stats.append(box.get("m", 0.0))
+    return torch.cat(outs, 0), stats
+
+
+def _run(q, k, v, H, scale, w, g, stat, idx=None):
+    dev = "cuda"
+    gs = torch.tensor([g], dtype=torch.float32, device=dev)
+    out, st = A.cross_attention(q.to(dev), k.to(dev), v.to(dev), H, scale,
+                                None if w is None else w.to(dev), None if idx is None else idx.to(dev),
+                                _native.PWW_STAT_MAX if stat == "max" else _native.PWW_STAT_STD, gs, return_stats=True)
+    torch.cuda.synchronize()
+    return out.float().cpu(), (None if st is None else st.cpu())
+
+
+@pytest.mark.parametrize("N,H,D", SD15_512 + SD15_256 + SD21_768 + RAGGED)
+@pytest.mark.parametrize("stat", ["max", "std"])
+def test_bias_path_matches_oracle(N, H, D, stat):
+    if stat == "std" and N * H > 40000:
+        pytest.skip("std covered at the smaller sizes; max covers the large ones")
+    T, B = 77, 1
+    q, k, v, w = _inputs(B, N, H, D, T, seed=N * 131 + D)
+    scale = D ** -0.5
+    g = 0.4 * math.log(1 + 7.0) if stat == "max" else 0.5 * math.log(1 + 7.0 ** 2)
+    got, st = _run(q, k, v, H, scale, w, g, stat)
+    ref16, st16 = _oracle(q, k, v, H, scale, w, g, stat, emulate=True)
+    ref32, _ = _oracle(q, k, v, H, scale, w, g, stat, emulate=False)
+    if N * H * T > 1:
+        assert abs(float(st[0]) - st16[0]) <= 2 ** -10 * abs(st16[0]) + 1e-6, (float(st[0]), st16[0])
+    amax = ref32.abs().max().item()
+    assert (got - ref16).abs().max().item() <= 1e-3 * amax
+    assert (got - ref32).abs().max().item() <= 2e-3 * amax
+
+
+@pytest.mark.parametrize("N,H,D", [(4096, 8, 40), (64, 8, 160), (576, 20, 64)])
+def test_plain_cross_attention_matches_oracle(N, H, D):
+    """Tensor context / uncond dict: no bias (paint_with_words.py:107-110)."""
+    q, k, v, _ = _inputs(2, N, H, D, 77, seed=7)
+    got, st = _run(q, k, v, H, D ** -0.5, None, 0.0, "max")
+    ref32, _ = _oracle(q, k, v, H, D ** -0.5, None, 0.0, "max", emulate=False)
+    assert st is None
+    assert (got - ref32).abs().max().item() <= 2e-3 * ref32.abs().max().item()
+
+
+@pytest.mark.parametrize("T", [1, 16, 77, 80, 128])
+def test_key_lengths(T):
+    N, H, D = 256, 8, 40
+    q, k, v, w = _inputs(1, N, H, D, T, seed=T)
+    g = 0.7
+    got, st = _run(q, k, v, H, D ** -0.5, w, g, "max")
+    ref32, st32 = _oracle(q, k, v, H, D ** -0.5, w, g, "max", emulate=False)
+    assert (got - ref32).abs().max().item() <= 2e-3 * ref32.abs().max().item()
+
+
+def test_batched_cfg_semantics_per_image_stats():
+    """[cond0, uncond, cond1] in one call: per-image statistic, index -1 = no bias, maps picked by index."""
+    N, H, D, T = 1024, 8, 80, 77
+    q, k, v, w = _inputs(3, N, H, D, T, seed=99)
+    q[2] *= 3.0                                     # make the images' maxima very different
+    idx = torch.tensor([1, -1, 0], dtype=torch.int32)
+    g = 0.4 * math.log(1 + 3.0)
+    got, st = _run(q, k, v, H, D ** -0.5, w[:2].contiguous(), g, "max", idx)
+    w_eff = torch.stack([w[1], torch.zeros_like(w[0]), w[0]])
+    ref, stats = _oracle(q, k, v, H, D ** -0.5, w_eff, g, "max", emulate=False)
+    ref_plain, _ = _oracle(q[1:2], k[1:2], v[1:2], H, D ** -0.5, None, 0.0, "max", emulate=False)
+    amax = ref.abs().max().item()
+    assert (got[0] - ref[0]).abs().max().item() <= 2e-3 * amax
+    assert (got[2] - ref[2]).abs().max().item() <= 2e-3 * amax
+    assert (got[1] - ref_plain[0]).abs().max().item() <= 2e-3 * amax
+    assert float(st[1]) == 0.0 and abs(float(st[2]) - stats[2]) <= 2e-3 * abs(stats[2])
+    # batching does not change an image's result (sharding invariance): bit-identical
+    solo, _ = _run(q[2:3], k[2:3], v[2:3], H, D ** -0.5, w[0:1].contiguous(), g, "max")
+    assert torch.equal(solo[0], got[2])
+
+
+def test_strided_views_no_copy_semantics():
+    """q/k/v as column slices of one fused [B,L,3C] projection buffer (row stride 3C)."""
+    N, H, D, T = 256, 8, 40, 77
+    C = H * D
+    q, k, v, w = _inputs(1, N, H, D, T, seed=5)
+    kv = torch.cat([k, v], -1).cuda()               # [1,T,2C]
+    out = A.cross_attention(q.cuda(), kv[..., :C], kv[..., C:], H, D ** -0.5)
+    ref32, _ = _oracle(q, k, v, H, D ** -0.5, None, 0.0, "max", emulate=False)
+    assert (out.float().cpu() - ref32).abs().max().item() <= 2e-3 * ref32.abs().max().item()
+
+
+def test_stats_workspace_is_self_cleaning():
+    N, H, D = 1024, 8, 80
+    q, k, v, w = _inputs(2, N, H, D, 77, seed=3)
+    a, sa = _run(q, k, v, H, D ** -0.5, w, 0.5, "std")
+    b, sb = _run(q, k, v, H, D ** -0.5, w, 0.5, "std")
+    assert torch.equal(a, b) and torch.equal(sa, sb)          # deterministic, counters reset
+
+
+def test_unsupported_shape_raises():
+    q = torch.zeros(1, 64, 96, dtype=torch.float16, device="cuda")
+    kv = torch.zeros(1, 77, 96, dtype=torch.float16, device="cuda")
+    with pytest.raises(_native.NativeError):
+        A.cross_attention(q, kv, kv, 2, 0.1)                  # D=48: no kernel, no fallback
+    kv = torch.zeros(1, 200, 80, dtype=torch.float16, device="cuda")
+    with pytest.raises(_native.NativeError):
+        A.cross_attention(torch.zeros(1, 64, 80, dtype=torch.float16, device="cuda"), kv, kv, 2, 0.1)   # T>128
+
+
+def test_real_weight_map_aurora(golden):
+    """aurora_1 map at N=4096 (config 2 of BASELINE.json), default-style weight function."""
+    mb = golden["mask_builder"]
+    w = torch.from_numpy(mb["aurora_512_w8"])[None]
+    q, k, v, _ = _inputs(1, 4096, 8, 40, 77, seed=2026)
+    g = 0.4 * math.log(1 + 14.6146)
+    got, st = _run(q, k, v, 8, 40 ** -0.5, w, g, "max")
+    ref32, stats = _oracle(q, k, v, 8, 40 ** -0.5, w, g, "max", emulate=False)
+    assert (got - ref32).abs().max().item() <= 2e-3 * ref32.abs().max().item()
