@@ -4,15 +4,14 @@
 
 #include "pww_common.cuh"
 #include "xattn_simt.cuh"
+#include "xattn_tc.cuh"
+#include <stdlib.h>
 
 namespace {
 
 thread_local char g_last_cuda_error[256] = "";
 
-int cuda_fail(cudaError_t e) {
-  snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
-  return PWW_ERR_CUDA;
-}
+int cuda_fail(cudaError_t e);
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -31,6 +30,23 @@ int check_common(const void* q, const void* k, int B, int H, int N, int T, int D
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int stats_ctas_per_image(int H, int N) { return H * pww::ceil_div(N, pww::simt::kRows); }
+
+// Partial slots reserved per image: covers the tcgen05 kernel (8 reducer warps x <=256 SMs) and the CUDA-core
+// kernel (one slot per CTA of the image).  Device independent so the size can be computed without a GPU.
+int stats_slots_per_image(int H, int N) {
+  int simt = stats_ctas_per_image(H, N);
+  return simt > 2048 ? simt : 2048;
+}
+
+// tcgen05 path covers the Stable Diffusion key lengths (T <= 80); 81..128 keys run on the CUDA-core kernels.
+bool use_tc(int T) {
+  static int force_simt = -1;
+  if (force_simt < 0) {
+    const char* e = getenv("PWW_FORCE_SIMT");
+    force_simt = (e && e[0] == '1') ? 1 : 0;
+  }
+  return T <= pww::tc::kTP && !force_simt;
+}
 
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
@@ -61,6 +77,13 @@ int launch_fwd(const pww::XattnParams& p, cudaStream_t s) {
   pww::simt::xattn_fwd_kernel<D><<<grid, pww::simt::kRows, smem, s>>>(p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? PWW_OK : cuda_fail(e);
+}
+
+int cuda_fail(cudaError_t e) {
+  snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s %s", cudaGetErrorName(e), cudaGetErrorString(e),
+           pww::tc::tc_error_buf());
+  pww::tc::tc_error_buf()[0] = 0;
+  return PWW_ERR_CUDA;
 }
 
 }  // namespace
@@ -95,7 +118,7 @@ size_t pww_xattn_workspace_bytes(int B, int H, int N, int T, int D) {
   (void)T; (void)D;
   if (B <= 0 || H <= 0 || N <= 0) return 0;
   return align_up((size_t)B * sizeof(unsigned int), 256) +
-         (size_t)B * stats_ctas_per_image(H, N) * sizeof(pww::StatPartial);
+         (size_t)B * stats_slots_per_image(H, N) * sizeof(pww::StatPartial);
 }
 
 int pww_xattn_stats_f16(const void* q, const void* k, int B, int H, int N, int T, int D, int64_t q_batch_stride,
@@ -116,6 +139,17 @@ int pww_xattn_stats_f16(const void* q, const void* k, int B, int H, int N, int T
   p.partials = (pww::StatPartial*)((char*)workspace + align_up((size_t)B * sizeof(unsigned int), 256));
   p.ctas_per_image = stats_ctas_per_image(H, N);
   cudaStream_t s = (cudaStream_t)stream;
+  if (use_tc(T)) {
+    if (pww::tc::stats_slots() > stats_slots_per_image(H, N)) return PWW_ERR_WORKSPACE;
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (D) {
+      case 40: e = pww::tc::launch_stats<40>(p, s); break;
+      case 64: e = pww::tc::launch_stats<64>(p, s); break;
+      case 80: e = pww::tc::launch_stats<80>(p, s); break;
+      case 160: e = pww::tc::launch_stats<160>(p, s); break;
+    }
+    return e == cudaSuccess ? PWW_OK : cuda_fail(e);
+  }
   switch (D) {
     case 40: return launch_stats<40>(p, s);
     case 64: return launch_stats<64>(p, s);
@@ -144,6 +178,16 @@ int pww_xattn_fwd_f16(const void* q, const void* k, const void* v, void* out, in
   p.wmap = wmap; p.wmap_bs = wmap_batch_stride; p.wmap_index = wmap_index;
   p.stats = stats; p.g_sigma = g_sigma; p.scale = scale;
   cudaStream_t s = (cudaStream_t)stream;
+  if (use_tc(T)) {
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (D) {
+      case 40: e = pww::tc::launch_fwd<40>(p, s); break;
+      case 64: e = pww::tc::launch_fwd<64>(p, s); break;
+      case 80: e = pww::tc::launch_fwd<80>(p, s); break;
+      case 160: e = pww::tc::launch_fwd<160>(p, s); break;
+    }
+    return e == cudaSuccess ? PWW_OK : cuda_fail(e);
+  }
   switch (D) {
     case 40: return launch_fwd<40>(p, s);
     case 64: return launch_fwd<64>(p, s);
