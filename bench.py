@@ -310,7 +310,9 @@ def main():
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        torch.cuda.nvtx.range_push("pww_timed")
         run_steps(n, per_step)
+        torch.cuda.nvtx.range_pop()
         e1.record()
         torch.cuda.synchronize(device)
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)

@@ -141,14 +141,23 @@ int pww_xattn_stats_f16(const void* q, const void* k, int B, int H, int N, int T
   cudaStream_t s = (cudaStream_t)stream;
   if (use_tc(T)) {
     if (pww::tc::stats_slots() > stats_slots_per_image(H, N)) return PWW_ERR_WORKSPACE;
-    cudaError_t e = cudaErrorInvalidValue;
-    switch (D) {
-      case 40: e = pww::tc::launch_stats<40>(p, s); break;
-      case 64: e = pww::tc::launch_stats<64>(p, s); break;
-      case 80: e = pww::tc::launch_stats<80>(p, s); break;
-      case 160: e = pww::tc::launch_stats<160>(p, s); break;
+    for (int b0 = 0; b0 < B; b0 += pww::tc::kMaxBatch) {          // <= 256 images per launch
+      pww::XattnParams c = p;
+      c.B = (B - b0) < pww::tc::kMaxBatch ? (B - b0) : pww::tc::kMaxBatch;
+      c.q = p.q + (int64_t)b0 * p.q_bs;
+      c.k = p.k + (int64_t)b0 * p.k_bs;
+      c.wmap_index = p.wmap_index ? p.wmap_index + b0 : nullptr;
+      c.stats_out = p.stats_out + b0;
+      cudaError_t e = cudaErrorInvalidValue;
+      switch (D) {
+        case 40: e = pww::tc::launch_stats<40>(c, s); break;
+        case 64: e = pww::tc::launch_stats<64>(c, s); break;
+        case 80: e = pww::tc::launch_stats<80>(c, s); break;
+        case 160: e = pww::tc::launch_stats<160>(c, s); break;
+      }
+      if (e != cudaSuccess) return cuda_fail(e);
     }
-    return e == cudaSuccess ? PWW_OK : cuda_fail(e);
+    return PWW_OK;
   }
   switch (D) {
     case 40: return launch_stats<40>(p, s);
@@ -179,14 +188,26 @@ int pww_xattn_fwd_f16(const void* q, const void* k, const void* v, void* out, in
   p.stats = stats; p.g_sigma = g_sigma; p.scale = scale;
   cudaStream_t s = (cudaStream_t)stream;
   if (use_tc(T)) {
-    cudaError_t e = cudaErrorInvalidValue;
-    switch (D) {
-      case 40: e = pww::tc::launch_fwd<40>(p, s); break;
-      case 64: e = pww::tc::launch_fwd<64>(p, s); break;
-      case 80: e = pww::tc::launch_fwd<80>(p, s); break;
-      case 160: e = pww::tc::launch_fwd<160>(p, s); break;
+    for (int b0 = 0; b0 < B; b0 += pww::tc::kMaxBatch) {          // <= 256 images per launch
+      pww::XattnParams c = p;
+      c.B = (B - b0) < pww::tc::kMaxBatch ? (B - b0) : pww::tc::kMaxBatch;
+      c.q = p.q + (int64_t)b0 * p.q_bs;
+      c.k = p.k + (int64_t)b0 * p.k_bs;
+      c.v = p.v + (int64_t)b0 * p.k_bs;
+      c.out = p.out + (int64_t)b0 * p.o_bs;
+      c.wmap_index = (p.wmap && p.wmap_index) ? p.wmap_index + b0 : nullptr;
+      c.stats = p.stats ? p.stats + b0 : nullptr;
+      if (p.wmap && !p.wmap_index) c.wmap = p.wmap + (int64_t)b0 * p.wmap_bs;   // identity mapping
+      cudaError_t e = cudaErrorInvalidValue;
+      switch (D) {
+        case 40: e = pww::tc::launch_fwd<40>(c, s); break;
+        case 64: e = pww::tc::launch_fwd<64>(c, s); break;
+        case 80: e = pww::tc::launch_fwd<80>(c, s); break;
+        case 160: e = pww::tc::launch_fwd<160>(c, s); break;
+      }
+      if (e != cudaSuccess) return cuda_fail(e);
     }
-    return e == cudaSuccess ? PWW_OK : cuda_fail(e);
+    return PWW_OK;
   }
   switch (D) {
     case 40: return launch_fwd<40>(p, s);
@@ -195,6 +216,13 @@ int pww_xattn_fwd_f16(const void* q, const void* k, const void* v, void* out, in
     case 160: return launch_fwd<160>(p, s);
   }
   return PWW_ERR_UNSUPPORTED;
+}
+
+// Test infrastructure (not declared in the public header): point the kernels' debug timeline at a device buffer of
+// kTlTags*kTlIts int64 clock64 stamps [tag][iteration] written by CTA 0; pass NULL to disable.
+int pww_debug_set_timeline(void* device_buffer) {
+  pww::tc::debug_timeline() = (long long*)device_buffer;
+  return PWW_OK;
 }
 
 int pww_attn_fwd_f16(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int D,
