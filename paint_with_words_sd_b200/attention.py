@@ -151,10 +151,10 @@ def cross_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: in
     return out
 
 
-# Self-attention: the native flash kernel when libpww_b200 provides it for the shape; until then the
-# library attention of torch is the declared stand-in.  bench.py records
-# which one ran in `config.self_attn`.
-SELF_ATTN_IMPL = "torch-sdpa"
+# Self-attention (context=None): pww_attn_fwd_f16, the tcgen05 flash-attention kernel of libpww_b200.
+# SELF_ATTN_IMPL = "torch-sdpa" switches to torch's library attention -- a comparison knob for tests/bench only;
+# bench.py records which one ran in `config.self_attn`.
+SELF_ATTN_IMPL = "native"
 
 
 def self_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: float) -> torch.Tensor:

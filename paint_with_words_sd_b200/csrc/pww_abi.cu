@@ -5,6 +5,7 @@
 #include "pww_common.cuh"
 #include "xattn_simt.cuh"
 #include "xattn_tc.cuh"
+#include "attn_tc.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -228,9 +229,20 @@ int pww_debug_set_timeline(void* device_buffer) {
 int pww_attn_fwd_f16(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int D,
                      int64_t qkv_batch_stride, int64_t qkv_row_stride, int64_t o_batch_stride, int64_t o_row_stride,
                      float scale, void* stream) {
-  (void)q; (void)k; (void)v; (void)out; (void)B; (void)H; (void)N; (void)D; (void)qkv_batch_stride;
-  (void)qkv_row_stride; (void)o_batch_stride; (void)o_row_stride; (void)scale; (void)stream;
-  return PWW_ERR_UNSUPPORTED;  // tcgen05 flash kernel lands in attn_tc.cuh
+  if (!q || !k || !v || !out || B <= 0 || H <= 0 || N <= 0 || D <= 0) return PWW_ERR_BAD_ARG;
+  if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(out)) return PWW_ERR_BAD_ARG;
+  if ((qkv_batch_stride | qkv_row_stride | o_batch_stride | o_row_stride) & 7) return PWW_ERR_BAD_ARG;
+  if (qkv_row_stride < (int64_t)H * D || o_row_stride < (int64_t)H * D) return PWW_ERR_BAD_ARG;
+  if (!supported_head_dim(D)) return PWW_ERR_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaErrorInvalidValue;
+  switch (D) {
+    case 40: e = pww::fa::launch<40>(q, k, v, out, B, H, N, qkv_batch_stride, qkv_row_stride, o_batch_stride, o_row_stride, scale, s); break;
+    case 64: e = pww::fa::launch<64>(q, k, v, out, B, H, N, qkv_batch_stride, qkv_row_stride, o_batch_stride, o_row_stride, scale, s); break;
+    case 80: e = pww::fa::launch<80>(q, k, v, out, B, H, N, qkv_batch_stride, qkv_row_stride, o_batch_stride, o_row_stride, scale, s); break;
+    case 160: e = pww::fa::launch<160>(q, k, v, out, B, H, N, qkv_batch_stride, qkv_row_stride, o_batch_stride, o_row_stride, scale, s); break;
+  }
+  return e == cudaSuccess ? PWW_OK : cuda_fail(e);
 }
 
 }  // extern "C"
