@@ -278,6 +278,7 @@ def main():
         with torch.device(device):
             unet = P.unet.UNet2DConditionModel(UNetConfig.sd15()).half().eval().requires_grad_(False)
     bcast_bytes = sharding.broadcast_module_weights(unet, src=0)
+    unet = unet.to(memory_format=torch.channels_last)
     P.patch_unet(unet)
 
     tok, enc = SimpleWordTokenizer(), RandomTextEncoder(768).to(device)

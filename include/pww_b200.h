@@ -104,6 +104,22 @@ int pww_attn_fwd_f16(const void* q, const void* k, const void* v, void* out,
                      int64_t o_batch_stride, int64_t o_row_stride,
                      float scale, void* stream);
 
+/*
+ * Fused memory-bound ops of the UNet that calls the attention path (the reference gets them from diffusers/ATen as
+ * separate eager launches): channels-last fp16 activations, deterministic reductions.
+ *
+ * GroupNorm over [B, HW, C] (channels last) with G groups:  y = act((x + add[b,c] - mean) * rstd * gamma + beta),
+ * `add` ([B, C], may be NULL) is the ResNet block's time-embedding term (added before normalisation), act = SiLU when
+ * `silu` != 0.  Needs C % 8 == 0, C % G == 0, G <= 64 and pww_groupnorm_workspace_bytes() of scratch.
+ */
+size_t pww_groupnorm_workspace_bytes(int B, int HW, int G);
+int pww_groupnorm_nhwc_f16(const void* x, const void* add, const void* gamma, const void* beta, void* y,
+                           int B, int HW, int C, int G, float eps, int silu,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* GEGLU: out[m, i] = in[m, i] * gelu(in[m, I + i]) for in [M, 2*I], out [M, I] (exact erf GELU); I % 8 == 0. */
+int pww_geglu_f16(const void* in, void* out, int64_t M, int I, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,7 @@
 #include "xattn_simt.cuh"
 #include "xattn_tc.cuh"
 #include "attn_tc.cuh"
+#include "unet_ops.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -217,6 +218,48 @@ int pww_xattn_fwd_f16(const void* q, const void* k, const void* v, void* out, in
     case 160: return launch_fwd<160>(p, s);
   }
   return PWW_ERR_UNSUPPORTED;
+}
+
+size_t pww_groupnorm_workspace_bytes(int B, int HW, int G) {
+  if (B <= 0 || HW <= 0 || G <= 0) return 0;
+  return (size_t)B * pww::uops::gn_chunks(HW) * G * 2 * sizeof(float);
+}
+
+int pww_groupnorm_nhwc_f16(const void* x, const void* add, const void* gamma, const void* beta, void* y, int B, int HW,
+                           int C, int G, float eps, int silu, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!x || !gamma || !beta || !y || !workspace || B <= 0 || HW <= 0 || C <= 0 || G <= 0) return PWW_ERR_BAD_ARG;
+  if (!aligned16(x) || !aligned16(y) || (add && !aligned16(add))) return PWW_ERR_BAD_ARG;
+  if ((C & 7) || (C % G) || G > 64 || (C >> 3) > 1024) return PWW_ERR_UNSUPPORTED;
+  if (workspace_bytes < pww_groupnorm_workspace_bytes(B, HW, G)) return PWW_ERR_WORKSPACE;
+  pww::uops::GnParams p;
+  p.x = (const __half*)x; p.add = (const __half*)add; p.gamma = (const __half*)gamma; p.beta = (const __half*)beta;
+  p.y = (__half*)y; p.partial = (float*)workspace;
+  p.B = B; p.HW = HW; p.C = C; p.G = G; p.eps = eps; p.silu = silu;
+  p.chunks = pww::uops::gn_chunks(HW);
+  p.rows_per_chunk = (HW + p.chunks - 1) / p.chunks;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nvec = C >> 3;
+  const int rpp = nvec >= 256 ? 1 : 256 / nvec;
+  const size_t smem1 = (size_t)rpp * C * 2 * sizeof(float);
+  if (smem1 > 48 * 1024) return PWW_ERR_UNSUPPORTED;
+  pww::uops::gn_stats_kernel<<<dim3(p.chunks, B), nvec * rpp, smem1, s>>>(p);
+  const int rows_per_block = 32;
+  pww::uops::gn_apply_kernel<<<dim3((HW + rows_per_block - 1) / rows_per_block, B), 256, (size_t)C * 2 * sizeof(float), s>>>(
+      p, rows_per_block);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? PWW_OK : cuda_fail(e);
+}
+
+int pww_geglu_f16(const void* in, void* out, int64_t M, int I, void* stream) {
+  if (!in || !out || M <= 0 || I <= 0 || !aligned16(in) || !aligned16(out)) return PWW_ERR_BAD_ARG;
+  if (I & 7) return PWW_ERR_UNSUPPORTED;
+  const long long total = (long long)M * (I >> 3);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)pww::tc::num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  pww::uops::geglu_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)in, (__half*)out, M, I);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? PWW_OK : cuda_fail(e);
 }
 
 // Test infrastructure (not declared in the public header): point the kernels' debug timeline at a device buffer of

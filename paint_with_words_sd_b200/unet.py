@@ -26,6 +26,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import fused_ops
+
 
 @dataclass
 class UNetConfig:
@@ -99,7 +101,10 @@ class GEGLU(nn.Module):
         self.proj = nn.Linear(dim_in, dim_out * 2)
 
     def forward(self, x):
-        x, gate = self.proj(x).chunk(2, dim=-1)
+        h = self.proj(x)
+        if fused_ops.is_fast(h):
+            return fused_ops.geglu(h)              # one launch instead of chunk + gelu + mul
+        x, gate = h.chunk(2, dim=-1)
         return x * F.gelu(gate)
 
 
@@ -138,7 +143,23 @@ class Transformer2DModel(nn.Module):
         self.transformer_blocks = nn.ModuleList([BasicTransformerBlock(inner, heads, dim_head, cross_attention_dim)])
         self.proj_out = nn.Linear(inner, in_channels) if linear_proj else nn.Conv2d(inner, in_channels, 1)
 
+    def _forward_fast(self, x, encoder_hidden_states):
+        """Channels-last route: the token view [B,HW,C] of an NHWC activation is free, so GroupNorm is one fused
+        launch and the 1x1 projections are plain GEMMs -- no layout conversion anywhere."""
+        b, c, h, w = x.shape
+        res = x
+        t = fused_ops.group_norm_nhwc(x, self.norm, silu=False).permute(0, 2, 3, 1).reshape(b, h * w, c)
+        wi = self.proj_in.weight
+        t = F.linear(t, wi.reshape(wi.shape[0], wi.shape[1]), self.proj_in.bias)
+        for blk in self.transformer_blocks:
+            t = blk(t, context=encoder_hidden_states)
+        wo = self.proj_out.weight
+        t = F.linear(t, wo.reshape(wo.shape[0], wo.shape[1]), self.proj_out.bias)
+        return t.reshape(b, h, w, c).permute(0, 3, 1, 2) + res
+
     def forward(self, x, encoder_hidden_states=None):
+        if fused_ops.is_fast(x):
+            return self._forward_fast(x, encoder_hidden_states)
         b, c, h, w = x.shape
         res = x
         x = self.norm(x)
@@ -166,6 +187,12 @@ class ResnetBlock2D(nn.Module):
         self.conv_shortcut = nn.Conv2d(in_ch, out_ch, 1) if in_ch != out_ch else None
 
     def forward(self, x, temb):
+        if fused_ops.is_fast(x):
+            # GroupNorm+SiLU fused; the time-embedding add rides inside the second GroupNorm
+            h = self.conv1(fused_ops.group_norm_nhwc(x, self.norm1, silu=True))
+            t = self.time_emb_proj(F.silu(temb))
+            h = self.conv2(fused_ops.group_norm_nhwc(h, self.norm2, add=t, silu=True))
+            return (x if self.conv_shortcut is None else self.conv_shortcut(x)) + h
         h = self.conv1(F.silu(self.norm1(x)))
         h = h + self.time_emb_proj(F.silu(temb))[:, :, None, None]
         h = self.conv2(F.silu(self.norm2(h)))
@@ -309,7 +336,11 @@ class UNet2DConditionModel(nn.Module):
         wdtype = self.conv_in.weight.dtype
         temb = timestep_embedding(timestep, self.config.block_out_channels[0]).to(wdtype)
         temb = self.time_embedding["linear_2"](F.silu(self.time_embedding["linear_1"](temb)))
-        x = self.conv_in(sample.to(wdtype))
+        x = sample.to(wdtype)
+        fast = fused_ops.is_fast(x)
+        if fast:
+            x = x.contiguous(memory_format=torch.channels_last)
+        x = self.conv_in(x)
         skips = [x]
         for blk in self.down_blocks:
             x, outs = blk(x, temb, encoder_hidden_states)
@@ -317,7 +348,10 @@ class UNet2DConditionModel(nn.Module):
         x = self.mid_block(x, temb, encoder_hidden_states)
         for blk in self.up_blocks:
             x = blk(x, skips, temb, encoder_hidden_states)
-        x = self.conv_out(F.silu(self.conv_norm_out(x)))
+        if fast:
+            x = self.conv_out(fused_ops.group_norm_nhwc(x, self.conv_norm_out, silu=True))
+        else:
+            x = self.conv_out(F.silu(self.conv_norm_out(x)))
         return _Sample(x)
 
 
@@ -332,4 +366,7 @@ def build_unet(cfg: UNetConfig, seed: int = 0, dtype=torch.float32, device="cpu"
         torch.manual_seed(seed)
         unet = UNet2DConditionModel(cfg)
     unet.eval().requires_grad_(False)
-    return unet.to(device=device, dtype=dtype)
+    unet = unet.to(device=device, dtype=dtype)
+    if torch.device(device).type == "cuda":
+        unet = unet.to(memory_format=torch.channels_last)      # NHWC conv weights: no layout conversion kernels
+    return unet
