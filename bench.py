@@ -254,6 +254,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="timed region only (for ncu launch lists): no e2e/roofline/cpu legs")
     args = ap.parse_args()
     rank, local_rank, world = sharding.env_world()
     if args.impl == "reference":
@@ -332,6 +333,11 @@ def main():
             per_step_launches = (_native.launch_count - launches_before) // max(1, args.steps)
         value = world * args.steps / (ms / 1e3)
 
+        if args.quick:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms / args.steps,
+                                  "steps": args.steps, "quick": True}), flush=True)
+            return
         # ---- e2e: host buffers in, host buffer out, every step ----
         dev_in = sampler.device_inputs()
         pinned = {k: t.detach().to("cpu").pin_memory() for k, t in dev_in.items()}

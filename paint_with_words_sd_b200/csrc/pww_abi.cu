@@ -222,18 +222,26 @@ int pww_xattn_fwd_f16(const void* q, const void* k, const void* v, void* out, in
 
 size_t pww_groupnorm_workspace_bytes(int B, int HW, int G) {
   if (B <= 0 || HW <= 0 || G <= 0) return 0;
-  return (size_t)B * pww::uops::gn_chunks(HW) * G * 2 * sizeof(float);
+  return align_up((size_t)B * sizeof(unsigned int), 256) + align_up((size_t)B * G * 2 * sizeof(float), 256) +
+         (size_t)B * pww::uops::gn_chunks(HW) * G * 2 * sizeof(float);
 }
 
 int pww_groupnorm_nhwc_f16(const void* x, const void* add, const void* gamma, const void* beta, void* y, int B, int HW,
                            int C, int G, float eps, int silu, void* workspace, size_t workspace_bytes, void* stream) {
   if (!x || !gamma || !beta || !y || !workspace || B <= 0 || HW <= 0 || C <= 0 || G <= 0) return PWW_ERR_BAD_ARG;
-  if (!aligned16(x) || !aligned16(y) || (add && !aligned16(add))) return PWW_ERR_BAD_ARG;
+  if (!aligned16(x) || !aligned16(y) || !aligned16(gamma) || !aligned16(beta) || (add && !aligned16(add)))
+    return PWW_ERR_BAD_ARG;
   if ((C & 7) || (C % G) || G > 64 || (C >> 3) > 1024) return PWW_ERR_UNSUPPORTED;
   if (workspace_bytes < pww_groupnorm_workspace_bytes(B, HW, G)) return PWW_ERR_WORKSPACE;
   pww::uops::GnParams p;
   p.x = (const __half*)x; p.add = (const __half*)add; p.gamma = (const __half*)gamma; p.beta = (const __half*)beta;
-  p.y = (__half*)y; p.partial = (float*)workspace;
+  p.y = (__half*)y;
+  char* w = (char*)workspace;
+  p.counters = (unsigned int*)w;
+  w += align_up((size_t)B * sizeof(unsigned int), 256);
+  p.stats = (float*)w;
+  w += align_up((size_t)B * G * 2 * sizeof(float), 256);
+  p.partial = (float*)w;
   p.B = B; p.HW = HW; p.C = C; p.G = G; p.eps = eps; p.silu = silu;
   p.chunks = pww::uops::gn_chunks(HW);
   p.rows_per_chunk = (HW + p.chunks - 1) / p.chunks;
@@ -243,9 +251,11 @@ int pww_groupnorm_nhwc_f16(const void* x, const void* add, const void* gamma, co
   const size_t smem1 = (size_t)rpp * C * 2 * sizeof(float);
   if (smem1 > 48 * 1024) return PWW_ERR_UNSUPPORTED;
   pww::uops::gn_stats_kernel<<<dim3(p.chunks, B), nvec * rpp, smem1, s>>>(p);
-  const int rows_per_block = 32;
-  pww::uops::gn_apply_kernel<<<dim3((HW + rows_per_block - 1) / rows_per_block, B), 256, (size_t)C * 2 * sizeof(float), s>>>(
-      p, rows_per_block);
+  // enough row chunks to fill the machine even at 8x8 resolution
+  int rows_per_block = (int)(((long long)HW * B + 2 * pww::tc::num_sms() - 1) / (2 * pww::tc::num_sms()));
+  if (rows_per_block < rpp) rows_per_block = rpp;
+  if (rows_per_block > 32) rows_per_block = 32;
+  pww::uops::gn_apply_kernel<<<dim3((HW + rows_per_block - 1) / rows_per_block, B), nvec * rpp, 0, s>>>(p, rows_per_block);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? PWW_OK : cuda_fail(e);
 }

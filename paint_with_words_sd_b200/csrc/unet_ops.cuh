@@ -15,6 +15,8 @@ struct GnParams {
   const __half* beta;   // [C]
   __half* y;            // [B, HW, C]
   float* partial;       // [B, chunks, G, 2] (sum, sumsq) scratch
+  float* stats;         // [B, G, 2] (mean, rstd), written by the last stats block of each image
+  unsigned int* counters;  // [B] arrival counters (zero on entry, zero on exit)
   int B, HW, C, G, chunks, rows_per_chunk, silu;
   float eps;
 };
@@ -37,15 +39,26 @@ __global__ void gn_stats_kernel(GnParams p) {
     for (int i = 0; i < 4; ++i) { float2 f = __half22float2(ah[i]); a[2 * i] = f.x; a[2 * i + 1] = f.y; }
   }
   const __half* xb = p.x + (size_t)b * p.HW * p.C;
-  for (int r = r0 + rl; r < r1; r += rpp) {
-    const uint4 xv = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)r * p.C) + v);
-    const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+  // 4 independent 16-byte loads in flight per thread
+  for (int r = r0 + rl; r < r1; r += 4 * rpp) {
+    uint4 xv[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float2 f = __half22float2(xh[i]);
-      const float x0 = f.x + a[2 * i], x1 = f.y + a[2 * i + 1];
-      s[2 * i] += x0; q[2 * i] = fmaf(x0, x0, q[2 * i]);
-      s[2 * i + 1] += x1; q[2 * i + 1] = fmaf(x1, x1, q[2 * i + 1]);
+    for (int u = 0; u < 4; ++u) {
+      const int rr = r + u * rpp;
+      xv[u] = rr < r1 ? __ldg(reinterpret_cast<const uint4*>(xb + (size_t)rr * p.C) + v) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (r + u * rpp < r1) {
+        const __half2* xh = reinterpret_cast<const __half2*>(&xv[u]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float2 f = __half22float2(xh[i]);
+          const float x0 = f.x + a[2 * i], x1 = f.y + a[2 * i + 1];
+          s[2 * i] += x0; q[2 * i] = fmaf(x0, x0, q[2 * i]);
+          s[2 * i + 1] += x1; q[2 * i + 1] = fmaf(x1, x1, q[2 * i + 1]);
+        }
+      }
     }
   }
   // per-thread channel sums -> shared [rl][c]
@@ -63,54 +76,76 @@ __global__ void gn_stats_kernel(GnParams p) {
     float* out = p.partial + (((size_t)b * p.chunks + chunk) * p.G + g) * 2;
     out[0] = ts; out[1] = tq;
   }
+  // the last block of this image reduces the chunk partials in a fixed order -> (mean, rstd) per group
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(&p.counters[b], 1u) == (unsigned)p.chunks - 1u) ? 1 : 0;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int g = warp; g < p.G; g += nwarps) {
+    const float* pp = p.partial + ((size_t)b * p.chunks * p.G + g) * 2;
+    float ts = 0.f, tq = 0.f;
+    for (int c = lane; c < p.chunks; c += 32) { ts += __ldcg(pp + (size_t)c * p.G * 2); tq += __ldcg(pp + (size_t)c * p.G * 2 + 1); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ts += __shfl_xor_sync(0xffffffffu, ts, o);
+      tq += __shfl_xor_sync(0xffffffffu, tq, o);
+    }
+    if (lane == 0) {
+      const float n = (float)p.HW * (float)cg;
+      const float mean = ts / n;
+      float var = tq / n - mean * mean;
+      var = var < 0.f ? 0.f : var;
+      p.stats[((size_t)b * p.G + g) * 2] = mean;
+      p.stats[((size_t)b * p.G + g) * 2 + 1] = rsqrtf(var + p.eps);
+    }
+  }
+  if (threadIdx.x == 0) p.counters[b] = 0u;
 }
 
-// pass 2: y = act((x + add - mean) * rstd * gamma + beta).  grid (row blocks, B); block = 256
+// pass 2: y = act((x + add - mean) * rstd * gamma + beta).  grid (row chunks, B); block = nvec * rpp threads: a thread
+// keeps ONE 8-channel vector column, so its scale/shift live in registers and the row loop is pure streaming.
 __global__ void gn_apply_kernel(GnParams p, int rows_per_block) {
-  extern __shared__ float sm[];                 // scale[C], shift[C]
-  float* scale = sm;
-  float* shift = sm + p.C;
-  __shared__ float gmean[64], grstd[64];
+  const int nvec = p.C >> 3;
+  const int rpp = blockDim.x / nvec;
+  const int v = threadIdx.x % nvec, rl = threadIdx.x / nvec;
   const int b = blockIdx.y;
   const int cg = p.C / p.G;
-  for (int g = threadIdx.x; g < p.G; g += blockDim.x) {
-    double ts = 0.0, tq = 0.0;
-    const float* pp = p.partial + ((size_t)b * p.chunks * p.G + g) * 2;
-    for (int c = 0; c < p.chunks; ++c) { ts += pp[(size_t)c * p.G * 2]; tq += pp[(size_t)c * p.G * 2 + 1]; }
-    const double n = (double)p.HW * cg;
-    const double mean = ts / n;
-    double var = tq / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    gmean[g] = (float)mean;
-    grstd[g] = (float)(1.0 / sqrt(var + (double)p.eps));
+  float sc[8], sh[8];
+  {
+    const uint4 gv = __ldg(reinterpret_cast<const uint4*>(p.gamma) + v);
+    const uint4 bv = __ldg(reinterpret_cast<const uint4*>(p.beta) + v);
+    uint4 av = make_uint4(0, 0, 0, 0);
+    if (p.add) av = __ldg(reinterpret_cast<const uint4*>(p.add + (size_t)b * p.C) + v);
+    const __half* gh = reinterpret_cast<const __half*>(&gv);
+    const __half* bh = reinterpret_cast<const __half*>(&bv);
+    const __half* ah = reinterpret_cast<const __half*>(&av);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int g = (v * 8 + i) / cg;
+      const float mean = __ldg(p.stats + ((size_t)b * p.G + g) * 2), rstd = __ldg(p.stats + ((size_t)b * p.G + g) * 2 + 1);
+      sc[i] = rstd * __half2float(gh[i]);
+      sh[i] = __half2float(bh[i]) + (__half2float(ah[i]) - mean) * sc[i];
+    }
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-    const int g = c / cg;
-    const float sc = grstd[g] * __half2float(p.gamma[c]);
-    const float ad = p.add ? __half2float(p.add[(size_t)b * p.C + c]) : 0.f;
-    scale[c] = sc;
-    shift[c] = __half2float(p.beta[c]) + (ad - gmean[g]) * sc;
-  }
-  __syncthreads();
-  const int nvec = p.C >> 3;
   const int r0 = blockIdx.x * rows_per_block, r1 = min(p.HW, r0 + rows_per_block);
   const __half* xb = p.x + (size_t)b * p.HW * p.C;
   __half* yb = p.y + (size_t)b * p.HW * p.C;
-  const int total = (r1 - r0) * nvec;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int r = r0 + i / nvec, v = i % nvec;
+  for (int r = r0 + rl; r < r1; r += rpp) {
     const uint4 xv = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)r * p.C) + v);
     const __half2* xh = reinterpret_cast<const __half2*>(&xv);
     __align__(16) __half2 o[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      float2 f = __half22float2(xh[k]);
-      float y0 = fmaf(f.x, scale[v * 8 + 2 * k], shift[v * 8 + 2 * k]);
-      float y1 = fmaf(f.y, scale[v * 8 + 2 * k + 1], shift[v * 8 + 2 * k + 1]);
+      const float2 f = __half22float2(xh[k]);
+      float y0 = fmaf(f.x, sc[2 * k], sh[2 * k]);
+      float y1 = fmaf(f.y, sc[2 * k + 1], sh[2 * k + 1]);
       if (p.silu) {
-        y0 = y0 / (1.f + __expf(-y0));
-        y1 = y1 / (1.f + __expf(-y1));
+        y0 = __fdividef(y0, 1.f + __expf(-y0));
+        y1 = __fdividef(y1, 1.f + __expf(-y1));
       }
       o[k] = __floats2half2_rn(y0, y1);
     }
@@ -142,9 +177,9 @@ __global__ void geglu_kernel(const __half* __restrict__ in, __half* __restrict__
 }
 
 inline int gn_chunks(int HW) {
-  int rows = 64;
+  int rows = 16;
   int c = (HW + rows - 1) / rows;
-  return c < 1 ? 1 : (c > 256 ? 256 : c);
+  return c < 1 ? 1 : (c > 512 ? 512 : c);
 }
 
 }  // namespace uops

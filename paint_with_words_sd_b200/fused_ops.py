@@ -17,7 +17,7 @@ _WS: Dict[torch.device, torch.Tensor] = {}
 def _workspace(device, nbytes: int) -> torch.Tensor:
     w = _WS.get(device)
     if w is None or w.numel() < nbytes:
-        w = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        w = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)   # counters must start at zero
         _WS[device] = w
     return w
 
