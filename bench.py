@@ -84,7 +84,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "25", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -265,6 +265,7 @@ def main():
     args.warmup = max(args.warmup, 3)
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
+    os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: one JSON line only
     sharding.init_distributed("nccl")
     import torch.distributed as dist
     import paint_with_words_sd_b200 as P

@@ -121,6 +121,12 @@ int pww_groupnorm_nhwc_f16(const void* x, const void* add, const void* gamma, co
 /* GEGLU: out[m, i] = in[m, i] * gelu(in[m, I + i]) for in [M, 2*I], out [M, I] (exact erf GELU); I % 8 == 0. */
 int pww_geglu_f16(const void* in, void* out, int64_t M, int I, void* stream);
 
+/* Residual add + LayerNorm over the last dim of [M, C]:  s = x + res (res may be NULL);  sum_out = s (may be NULL);
+ * y = LayerNorm(s) * gamma + beta.  The transformer block's "x = attn(...) + x; h = norm(x)" pair in one pass.
+ * C % 8 == 0, C <= 2048. */
+int pww_add_layernorm_f16(const void* x, const void* res, const void* gamma, const void* beta, void* sum_out, void* y,
+                          int64_t M, int C, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,7 +17,7 @@ PWW_STAT_MAX, PWW_STAT_STD = 0, 1
 EXPORTS = (
     "pww_version", "pww_status_str", "pww_last_cuda_error", "pww_device_supported",
     "pww_xattn_workspace_bytes", "pww_xattn_stats_f16", "pww_xattn_fwd_f16", "pww_attn_fwd_f16",
-    "pww_groupnorm_workspace_bytes", "pww_groupnorm_nhwc_f16", "pww_geglu_f16",
+    "pww_groupnorm_workspace_bytes", "pww_groupnorm_nhwc_f16", "pww_geglu_f16", "pww_add_layernorm_f16",
 )
 
 
@@ -60,6 +60,8 @@ def lib() -> ctypes.CDLL:
     L.pww_groupnorm_nhwc_f16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i, c_i, c_i, c_f, c_i, c_vp, c_sz, c_vp]
     L.pww_geglu_f16.restype = c_i
     L.pww_geglu_f16.argtypes = [c_vp, c_vp, c_i64, c_i, c_vp]
+    L.pww_add_layernorm_f16.restype = c_i
+    L.pww_add_layernorm_f16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i, c_f, c_vp]
     _lib = L
     return L
 

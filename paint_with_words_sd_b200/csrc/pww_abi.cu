@@ -272,6 +272,34 @@ int pww_geglu_f16(const void* in, void* out, int64_t M, int I, void* stream) {
   return e == cudaSuccess ? PWW_OK : cuda_fail(e);
 }
 
+int pww_add_layernorm_f16(const void* x, const void* res, const void* gamma, const void* beta, void* sum_out, void* y,
+                          int64_t M, int C, float eps, void* stream) {
+  if (!x || !gamma || !beta || !y || M <= 0 || C <= 0) return PWW_ERR_BAD_ARG;
+  if (!aligned16(x) || !aligned16(y) || !aligned16(gamma) || !aligned16(beta) || (res && !aligned16(res)) ||
+      (sum_out && !aligned16(sum_out)))
+    return PWW_ERR_BAD_ARG;
+  if ((C & 7) || C > 2048) return PWW_ERR_UNSUPPORTED;
+  const int vpl = ((C >> 3) + 31) / 32;
+  const int warps = 8;
+  const unsigned grid = (unsigned)((M + warps - 1) / warps);
+  cudaStream_t s = (cudaStream_t)stream;
+  const __half *xp = (const __half*)x, *rp = (const __half*)res, *gp = (const __half*)gamma, *bp = (const __half*)beta;
+  __half *sp = (__half*)sum_out, *yp = (__half*)y;
+  switch (vpl) {
+    case 1: pww::uops::add_layernorm_kernel<1><<<grid, warps * 32, 0, s>>>(xp, rp, gp, bp, sp, yp, M, C, eps); break;
+    case 2: pww::uops::add_layernorm_kernel<2><<<grid, warps * 32, 0, s>>>(xp, rp, gp, bp, sp, yp, M, C, eps); break;
+    case 3: pww::uops::add_layernorm_kernel<3><<<grid, warps * 32, 0, s>>>(xp, rp, gp, bp, sp, yp, M, C, eps); break;
+    case 4: pww::uops::add_layernorm_kernel<4><<<grid, warps * 32, 0, s>>>(xp, rp, gp, bp, sp, yp, M, C, eps); break;
+    case 5: pww::uops::add_layernorm_kernel<5><<<grid, warps * 32, 0, s>>>(xp, rp, gp, bp, sp, yp, M, C, eps); break;
+    case 6: pww::uops::add_layernorm_kernel<6><<<grid, warps * 32, 0, s>>>(xp, rp, gp, bp, sp, yp, M, C, eps); break;
+    case 7: pww::uops::add_layernorm_kernel<7><<<grid, warps * 32, 0, s>>>(xp, rp, gp, bp, sp, yp, M, C, eps); break;
+    case 8: pww::uops::add_layernorm_kernel<8><<<grid, warps * 32, 0, s>>>(xp, rp, gp, bp, sp, yp, M, C, eps); break;
+    default: return PWW_ERR_UNSUPPORTED;
+  }
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? PWW_OK : cuda_fail(e);
+}
+
 // Test infrastructure (not declared in the public header): point the kernels' debug timeline at a device buffer of
 // kTlTags*kTlIts int64 clock64 stamps [tag][iteration] written by CTA 0; pass NULL to disable.
 int pww_debug_set_timeline(void* device_buffer) {

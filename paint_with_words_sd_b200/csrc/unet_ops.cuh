@@ -176,6 +176,76 @@ __global__ void geglu_kernel(const __half* __restrict__ in, __half* __restrict__
   }
 }
 
+// Fused residual add + LayerNorm over the last dim: s = x (+ res); sum_out = s (optional); y = LN(s) * gamma + beta.
+// One warp per row; a lane keeps its 16-byte vectors of the row in registers (C <= 2048), two-pass mean/variance.
+template <int VPL>   // vectors per lane
+__global__ void add_layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ res,
+                                     const __half* __restrict__ gamma, const __half* __restrict__ beta,
+                                     __half* __restrict__ sum_out, __half* __restrict__ y, long long M, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int nvec = C >> 3;
+  float v[VPL][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + row * C) + vi);
+      const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+      uint4 rv = make_uint4(0, 0, 0, 0);
+      if (res) rv = __ldg(reinterpret_cast<const uint4*>(res + row * C) + vi);
+      const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+      __align__(16) __half2 so[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 a = __half22float2(xh[k]), b = __half22float2(rh[k]);
+        // the residual stream is fp16 in the eager model too: round the sum once, then normalise the rounded value
+        so[k] = __floats2half2_rn(a.x + b.x, a.y + b.y);
+        const float2 f = __half22float2(so[k]);
+        v[i][2 * k] = f.x; v[i][2 * k + 1] = f.y;
+        sum += f.x + f.y;
+      }
+      if (sum_out) reinterpret_cast<uint4*>(sum_out + row * C)[vi] = *reinterpret_cast<const uint4*>(so);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[i][k] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    if (lane + i * 32 < nvec) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const float d = v[i][k] - mean; sq = fmaf(d, d, sq); }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gamma) + vi);
+      const uint4 bv = __ldg(reinterpret_cast<const uint4*>(beta) + vi);
+      const __half2* gh = reinterpret_cast<const __half2*>(&gv);
+      const __half2* bh = reinterpret_cast<const __half2*>(&bv);
+      __align__(16) __half2 o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 g = __half22float2(gh[k]), b = __half22float2(bh[k]);
+        o[k] = __floats2half2_rn((v[i][2 * k] - mean) * rstd * g.x + b.x, (v[i][2 * k + 1] - mean) * rstd * g.y + b.y);
+      }
+      reinterpret_cast<uint4*>(y + row * C)[vi] = *reinterpret_cast<const uint4*>(o);
+    }
+  }
+}
+
 inline int gn_chunks(int HW) {
   int rows = 16;
   int c = (HW + rows - 1) / rows;

@@ -58,3 +58,21 @@ def geglu(h: torch.Tensor) -> torch.Tensor:
     _native.check(rc, "pww_geglu_f16")
     _native.launch_count += 1
     return out
+
+
+def add_layer_norm(x: torch.Tensor, res: Optional[torch.Tensor], ln: torch.nn.LayerNorm, want_sum: bool = True):
+    """(s, y) with s = x + res (s is x itself when res is None) and y = LayerNorm(s); x, res: [..., C] fp16."""
+    if not x.is_contiguous():
+        x = x.contiguous()
+    if res is not None and not res.is_contiguous():
+        res = res.contiguous()
+    C = x.shape[-1]
+    M = x.numel() // C
+    y = torch.empty_like(x)
+    s = torch.empty_like(x) if (res is not None and want_sum) else None
+    rc = _native.lib().pww_add_layernorm_f16(x.data_ptr(), None if res is None else res.data_ptr(), ln.weight.data_ptr(),
+                                             ln.bias.data_ptr(), None if s is None else s.data_ptr(), y.data_ptr(), M, C,
+                                             float(ln.eps), torch.cuda.current_stream(x.device).cuda_stream)
+    _native.check(rc, "pww_add_layernorm_f16")
+    _native.launch_count += 1
+    return (x if res is None else s), y

@@ -128,6 +128,12 @@ class BasicTransformerBlock(nn.Module):
         self.norm1, self.norm2, self.norm3 = nn.LayerNorm(dim), nn.LayerNorm(dim), nn.LayerNorm(dim)
 
     def forward(self, x, context=None):
+        if fused_ops.is_fast(x):
+            # residual add fused into the following LayerNorm: 3 LN launches + 1 add instead of 3 LN + 3 adds
+            _, h = fused_ops.add_layer_norm(x, None, self.norm1)
+            x, h = fused_ops.add_layer_norm(self.attn1(h), x, self.norm2)
+            x, h = fused_ops.add_layer_norm(self.attn2(h, context=context), x, self.norm3)
+            return self.ff(h) + x
         x = self.attn1(self.norm1(x)) + x
         x = self.attn2(self.norm2(x), context=context) + x
         return self.ff(self.norm3(x)) + x

@@ -45,6 +45,23 @@ def test_geglu(M, I):
     assert (got - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("M,C", [(2 * 4096, 320), (2 * 1024, 640), (2 * 256, 1280), (5, 1280), (3, 8), (7, 2048)])
+@pytest.mark.parametrize("with_res", [True, False])
+def test_add_layer_norm(M, C, with_res):
+    g = torch.Generator().manual_seed(M + C)
+    x = (torch.randn(M, C, generator=g) * 2.0).half()
+    res = (torch.randn(M, C, generator=g) * 2.0).half() if with_res else None
+    ln = torch.nn.LayerNorm(C)
+    ln.weight.data = torch.randn(C, generator=g) * 0.5 + 1.0
+    ln.bias.data = torch.randn(C, generator=g) * 0.2
+    ln_h = ln.half().cuda()
+    s_ref = (x.float() + res.float()).half() if with_res else x
+    y_ref = F.layer_norm(s_ref.float(), (C,), ln_h.weight.float().cpu(), ln_h.bias.float().cpu(), ln.eps)
+    s, y = fused_ops.add_layer_norm(x.cuda(), None if res is None else res.cuda(), ln_h)
+    assert torch.equal(s.cpu(), s_ref)                      # the residual stream is bit-identical to an fp16 add
+    assert (y.float().cpu() - y_ref).abs().max().item() <= 4e-3 * max(1.0, y_ref.abs().max().item())
+
+
 def test_unet_fast_route_matches_plain_route():
     """Same fp16 weights: channels-last fused route vs the module-by-module PyTorch route (stock attention)."""
     cfg = UNetConfig.tiny()
