@@ -179,6 +179,28 @@ def self_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int
     return o.transpose(1, 2).reshape(B, N, C)
 
 
+def _fused_weight(module, attr: str, names) -> torch.Tensor:
+    """Row-concatenated projection weights (to_q|to_k|to_v or to_k|to_v), built once per module (inference weights
+    are static): one GEMM instead of two or three."""
+    w = getattr(module, attr, None)
+    ref = getattr(module, names[0]).weight
+    if w is None or w.device != ref.device or w.dtype != ref.dtype:
+        w = torch.cat([getattr(module, n).weight for n in names], 0).detach().contiguous()
+        object.__setattr__(module, attr, w)
+    return w
+
+
+def refresh_kv_cache(context: dict) -> None:
+    """Recompute cached context K/V in place after CONTEXT_TENSOR changed (same storage: graph-replay safe)."""
+    cache = context.get("KV_CACHE")
+    if not cache:
+        return
+    ctx = context["CONTEXT_TENSOR"]
+    with torch.autocast("cuda", dtype=torch.float16):
+        for module, kv in cache.values():
+            kv.copy_(F.linear(ctx, _fused_weight(module, "_pww_wkv", ("to_k", "to_v"))))
+
+
 def inj_forward(self, hidden_states, context=None, mask=None):
     """Replacement for `CrossAttention.__call__` (reference: paint_with_words.py:60-125)."""
     if not hidden_states.is_cuda:
@@ -189,10 +211,23 @@ def inj_forward(self, hidden_states, context=None, mask=None):
     else:
         ctx = context["CONTEXT_TENSOR"] if is_dict else context
 
+    C = self.to_q.weight.shape[0]
     with torch.autocast("cuda", dtype=torch.float16):
-        q = self.to_q(hidden_states)
-        k = self.to_k(ctx)
-        v = self.to_v(ctx)
+        if context is None:
+            # one [C -> 3C] GEMM; q/k/v are column views of its output (row stride 3C) -- the kernels take strides
+            qkv = F.linear(hidden_states, _fused_weight(self, "_pww_wqkv", ("to_q", "to_k", "to_v")))
+            q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+        else:
+            q = self.to_q(hidden_states)
+            cache = context.get("KV_CACHE") if is_dict else None
+            hit = cache.get(id(self)) if cache is not None else None
+            if hit is not None:
+                kv = hit[1]                          # K/V of the (step-invariant) text context, computed once
+            else:
+                kv = F.linear(ctx, _fused_weight(self, "_pww_wkv", ("to_k", "to_v")))
+                if cache is not None:
+                    cache[id(self)] = (self, kv)
+            k, v = kv[..., :C], kv[..., C:]
 
     if context is None:
         o = self_attention(q, k, v, self.heads, self.scale)

@@ -181,6 +181,7 @@ class PwWSampler:
         ctx["WMAP_INDEX"] = torch.tensor(list(range(m)) + [-1] * m, dtype=torch.int32, device=self.device)
         ctx["WEIGHT_FUNCTION"] = self.weight_function
         ctx["SIGMA"] = None
+        ctx["KV_CACHE"] = {}       # to_k/to_v of the text context are step-invariant: computed at the first step
         return ctx
 
     # -- one step, expressed only with device tensors / device scalars --------------------------
@@ -220,6 +221,8 @@ class PwWSampler:
         for k, h in pinned.items():
             dev[k].copy_(h, non_blocking=True)
             n += h.numel() * h.element_size()
+        if "CONTEXT_TENSOR" in pinned:
+            _attention.refresh_kv_cache(self._ctx)     # the cached K/V follow the new context
         return n
 
     def restart(self, latents: Optional[torch.Tensor] = None):
