@@ -109,12 +109,13 @@ int pww_attn_fwd_f16(const void* q, const void* k, const void* v, void* out,
  * separate eager launches): channels-last fp16 activations, deterministic reductions.
  *
  * GroupNorm over [B, HW, C] (channels last) with G groups:  y = act((x + add[b,c] - mean) * rstd * gamma + beta),
- * `add` ([B, C], may be NULL) is the ResNet block's time-embedding term (added before normalisation), act = SiLU when
+ * `add` ([B, C] with row stride `add_batch_stride`, may be NULL) is the ResNet block's time-embedding term (added before normalisation), act = SiLU when
  * `silu` != 0.  Needs C % 8 == 0, C % G == 0, G <= 64 and pww_groupnorm_workspace_bytes() of scratch that was
  * zero-filled once after allocation (self-cleaning arrival counters, like the attention statistics workspace).
  */
 size_t pww_groupnorm_workspace_bytes(int B, int HW, int G);
-int pww_groupnorm_nhwc_f16(const void* x, const void* add, const void* gamma, const void* beta, void* y,
+int pww_groupnorm_nhwc_f16(const void* x, const void* add, int64_t add_batch_stride /* elements */,
+                           const void* gamma, const void* beta, void* y,
                            int B, int HW, int C, int G, float eps, int silu,
                            void* workspace, size_t workspace_bytes, void* stream);
 

@@ -57,7 +57,7 @@ def lib() -> ctypes.CDLL:
     L.pww_groupnorm_workspace_bytes.restype = c_sz
     L.pww_groupnorm_workspace_bytes.argtypes = [c_i, c_i, c_i]
     L.pww_groupnorm_nhwc_f16.restype = c_i
-    L.pww_groupnorm_nhwc_f16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i, c_i, c_i, c_f, c_i, c_vp, c_sz, c_vp]
+    L.pww_groupnorm_nhwc_f16.argtypes = [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i, c_i, c_i, c_i, c_f, c_i, c_vp, c_sz, c_vp]
     L.pww_geglu_f16.restype = c_i
     L.pww_geglu_f16.argtypes = [c_vp, c_vp, c_i64, c_i, c_vp]
     L.pww_add_layernorm_f16.restype = c_i

@@ -226,15 +226,17 @@ size_t pww_groupnorm_workspace_bytes(int B, int HW, int G) {
          (size_t)B * pww::uops::gn_chunks(HW) * G * 2 * sizeof(float);
 }
 
-int pww_groupnorm_nhwc_f16(const void* x, const void* add, const void* gamma, const void* beta, void* y, int B, int HW,
-                           int C, int G, float eps, int silu, void* workspace, size_t workspace_bytes, void* stream) {
+int pww_groupnorm_nhwc_f16(const void* x, const void* add, int64_t add_batch_stride, const void* gamma, const void* beta,
+                           void* y, int B, int HW, int C, int G, float eps, int silu, void* workspace,
+                           size_t workspace_bytes, void* stream) {
   if (!x || !gamma || !beta || !y || !workspace || B <= 0 || HW <= 0 || C <= 0 || G <= 0) return PWW_ERR_BAD_ARG;
   if (!aligned16(x) || !aligned16(y) || !aligned16(gamma) || !aligned16(beta) || (add && !aligned16(add)))
     return PWW_ERR_BAD_ARG;
   if ((C & 7) || (C % G) || G > 64 || (C >> 3) > 1024) return PWW_ERR_UNSUPPORTED;
+  if (add && ((add_batch_stride & 7) || add_batch_stride < C)) return PWW_ERR_BAD_ARG;
   if (workspace_bytes < pww_groupnorm_workspace_bytes(B, HW, G)) return PWW_ERR_WORKSPACE;
   pww::uops::GnParams p;
-  p.x = (const __half*)x; p.add = (const __half*)add; p.gamma = (const __half*)gamma; p.beta = (const __half*)beta;
+  p.x = (const __half*)x; p.add = (const __half*)add; p.add_bs = add_batch_stride; p.gamma = (const __half*)gamma; p.beta = (const __half*)beta;
   p.y = (__half*)y;
   char* w = (char*)workspace;
   p.counters = (unsigned int*)w;

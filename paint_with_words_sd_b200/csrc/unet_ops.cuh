@@ -10,7 +10,8 @@ namespace uops {
 
 struct GnParams {
   const __half* x;      // [B, HW, C] channels-last activations
-  const __half* add;    // [B, C] or nullptr: per-image per-channel value added to x BEFORE normalisation
+  const __half* add;    // [B, C] (row stride add_bs) or nullptr: per-image per-channel value added BEFORE normalisation
+  long long add_bs;
   const __half* gamma;  // [C]
   const __half* beta;   // [C]
   __half* y;            // [B, HW, C]
@@ -33,7 +34,7 @@ __global__ void gn_stats_kernel(GnParams p) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; a[i] = 0.f; }
   if (p.add) {
-    const uint4 av = *reinterpret_cast<const uint4*>(p.add + (size_t)b * p.C + v * 8);
+    const uint4 av = *reinterpret_cast<const uint4*>(p.add + (size_t)b * p.add_bs + v * 8);
     const __half2* ah = reinterpret_cast<const __half2*>(&av);
 #pragma unroll
     for (int i = 0; i < 4; ++i) { float2 f = __half22float2(ah[i]); a[2 * i] = f.x; a[2 * i + 1] = f.y; }
@@ -119,7 +120,7 @@ __global__ void gn_apply_kernel(GnParams p, int rows_per_block) {
     const uint4 gv = __ldg(reinterpret_cast<const uint4*>(p.gamma) + v);
     const uint4 bv = __ldg(reinterpret_cast<const uint4*>(p.beta) + v);
     uint4 av = make_uint4(0, 0, 0, 0);
-    if (p.add) av = __ldg(reinterpret_cast<const uint4*>(p.add + (size_t)b * p.C) + v);
+    if (p.add) av = __ldg(reinterpret_cast<const uint4*>(p.add + (size_t)b * p.add_bs) + v);
     const __half* gh = reinterpret_cast<const __half*>(&gv);
     const __half* bh = reinterpret_cast<const __half*>(&bv);
     const __half* ah = reinterpret_cast<const __half*>(&av);

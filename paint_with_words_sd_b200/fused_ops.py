@@ -36,9 +36,12 @@ def group_norm_nhwc(x: torch.Tensor, gn: torch.nn.GroupNorm, add: Optional[torch
     y = torch.empty_like(x, memory_format=torch.channels_last)
     nbytes = L.pww_groupnorm_workspace_bytes(B, H * W, gn.num_groups)
     ws = _workspace(x.device, nbytes)
+    add_bs = 0
     if add is not None:
-        add = add.to(torch.float16).contiguous()
-    rc = L.pww_groupnorm_nhwc_f16(x.data_ptr(), None if add is None else add.data_ptr(), gn.weight.data_ptr(),
+        if add.dtype != torch.float16 or add.stride(-1) != 1 or (add.stride(0) % 8) or (add.data_ptr() % 16):
+            add = add.to(torch.float16).contiguous()
+        add_bs = add.stride(0)
+    rc = L.pww_groupnorm_nhwc_f16(x.data_ptr(), None if add is None else add.data_ptr(), add_bs, gn.weight.data_ptr(),
                                   gn.bias.data_ptr(), y.data_ptr(), B, H * W, C, gn.num_groups, float(gn.eps),
                                   1 if silu else 0, ws.data_ptr(), ws.numel(),
                                   torch.cuda.current_stream(x.device).cuda_stream)

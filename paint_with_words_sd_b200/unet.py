@@ -196,7 +196,9 @@ class ResnetBlock2D(nn.Module):
         if fused_ops.is_fast(x):
             # GroupNorm+SiLU fused; the time-embedding add rides inside the second GroupNorm
             h = self.conv1(fused_ops.group_norm_nhwc(x, self.norm1, silu=True))
-            t = self.time_emb_proj(F.silu(temb))
+            t = getattr(self, "_pww_t", None)       # slice of the UNet-wide batched projection, when provided
+            if t is None:
+                t = self.time_emb_proj(F.silu(temb))
             h = self.conv2(fused_ops.group_norm_nhwc(h, self.norm2, add=t, silu=True))
             return (x if self.conv_shortcut is None else self.conv_shortcut(x)) + h
         h = self.conv1(F.silu(self.norm1(x)))
@@ -346,6 +348,7 @@ class UNet2DConditionModel(nn.Module):
         fast = fused_ops.is_fast(x)
         if fast:
             x = x.contiguous(memory_format=torch.channels_last)
+            self._project_time_embeddings(temb)
         x = self.conv_in(x)
         skips = [x]
         for blk in self.down_blocks:
@@ -359,6 +362,30 @@ class UNet2DConditionModel(nn.Module):
         else:
             x = self.conv_out(F.silu(self.conv_norm_out(x)))
         return _Sample(x)
+
+
+def _resnets(unet: nn.Module):
+    return [m for m in unet.modules() if isinstance(m, ResnetBlock2D)]
+
+
+def _project_time_embeddings(self, temb):
+    """All 22 ResNet `time_emb_proj(silu(temb))` projections as ONE GEMM; each block reads its column slice."""
+    cache = self.__dict__.get("_pww_temb_w")
+    res = _resnets(self)
+    if cache is None or cache[0].device != temb.device or cache[0].dtype != temb.dtype:
+        w = torch.cat([r.time_emb_proj.weight for r in res], 0).detach().contiguous()
+        b = torch.cat([r.time_emb_proj.bias for r in res], 0).detach().contiguous()
+        cache = (w, b)
+        self.__dict__["_pww_temb_w"] = cache
+    t_all = F.linear(F.silu(temb), cache[0], cache[1])
+    off = 0
+    for r in res:
+        n = r.time_emb_proj.weight.shape[0]
+        object.__setattr__(r, "_pww_t", t_all[:, off:off + n])
+        off += n
+
+
+UNet2DConditionModel._project_time_embeddings = _project_time_embeddings
 
 
 def attention_modules(unet: nn.Module):

@@ -79,3 +79,6 @@ def test_unet_fast_route_matches_plain_route():
             fused_ops.is_fast = orig
     rel = ((fast - plain).pow(2).mean().sqrt() / plain.pow(2).mean().sqrt()).item()
     assert rel < 1e-2, rel
+    # leave no per-forward state behind for other tests
+    from paint_with_words_sd_b200.unet import _resnets
+    assert all(hasattr(r, "_pww_t") for r in _resnets(unet))
