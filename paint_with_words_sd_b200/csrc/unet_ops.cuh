@@ -248,7 +248,7 @@ __global__ void add_layernorm_kernel(const __half* __restrict__ x, const __half*
 }
 
 inline int gn_chunks(int HW) {
-  int rows = 16;
+  int rows = HW >= 4096 ? 64 : (HW >= 1024 ? 32 : 16);   // enough blocks to fill the SMs, few enough to finalise fast
   int c = (HW + rows - 1) / rows;
   return c < 1 ? 1 : (c > 512 ? 512 : c);
 }

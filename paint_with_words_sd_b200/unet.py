@@ -153,15 +153,17 @@ class Transformer2DModel(nn.Module):
         """Channels-last route: the token view [B,HW,C] of an NHWC activation is free, so GroupNorm is one fused
         launch and the 1x1 projections are plain GEMMs -- no layout conversion anywhere."""
         b, c, h, w = x.shape
-        res = x
+        if not x.is_contiguous(memory_format=torch.channels_last):
+            x = x.contiguous(memory_format=torch.channels_last)
+        res = x.permute(0, 2, 3, 1).reshape(b, h * w, c)           # token view of the NHWC activation (no copy)
         t = fused_ops.group_norm_nhwc(x, self.norm, silu=False).permute(0, 2, 3, 1).reshape(b, h * w, c)
         wi = self.proj_in.weight
         t = F.linear(t, wi.reshape(wi.shape[0], wi.shape[1]), self.proj_in.bias)
         for blk in self.transformer_blocks:
             t = blk(t, context=encoder_hidden_states)
         wo = self.proj_out.weight
-        t = F.linear(t, wo.reshape(wo.shape[0], wo.shape[1]), self.proj_out.bias)
-        return t.reshape(b, h, w, c).permute(0, 3, 1, 2) + res
+        t = F.linear(t, wo.reshape(wo.shape[0], wo.shape[1]), self.proj_out.bias) + res   # contiguous, vectorised add
+        return t.reshape(b, h, w, c).permute(0, 3, 1, 2)
 
     def forward(self, x, encoder_hidden_states=None):
         if fused_ops.is_fast(x):
