@@ -62,6 +62,16 @@ def workload_config(n_gpus: int) -> dict:
             "l2_policy": "inputs larger than L2: each step streams the 1.7 GB of fp16 UNet weights (L2 is 126 MB)"}
 
 
+def ncu_traffic(key: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+    (profiles/r01_xattn_traffic.json, produced from gpurun_out/r01_xattn_B*.ncu-rep); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_xattn_traffic.json")) as f:
+            return float(json.load(f)[key]["traffic_bytes"])
+    except Exception:
+        return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -378,13 +388,17 @@ def main():
             ach = r2["alg_bytes"] / (r2["us_fwd"] * 1e-6) / 1e9
             line["roofline"] = {
                 "kernel": "pww_xattn_fwd_f16 N=4096 C=320 H=8 T=77, B=2 (cond+uncond) as launched by this workload",
-                "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": ncu_traffic("B2_fwd"),
+                "traffic_note": "DRAM bytes per launch from profiles/r01_xattn_ncu_full_summary.txt (ncu --set full); below "
+                                "the algorithmic bytes because the O tile writes are still in L2 when the kernel ends",
                 "peak_source": peak_src, "us_per_launch": r2["us_fwd"], "alg_bytes_per_launch": r2["alg_bytes"],
                 "stats_kernel_us": r2["us_stats"],
                 "op_frac": r2["alg_bytes"] / ((r2["us_fwd"] + r2["us_stats"]) * 1e-6) / 1e9 / peak,
                 "batched": {"B": 16, "biased": 8, "us_fwd": r16["us_fwd"], "us_stats": r16["us_stats"],
                             "achieved": r16["alg_bytes"] / (r16["us_fwd"] * 1e-6) / 1e9,
                             "frac": r16["alg_bytes"] / (r16["us_fwd"] * 1e-6) / 1e9 / peak,
+                            "alg_bytes_per_launch": r16["alg_bytes"], "traffic": ncu_traffic("B16_fwd"),
                             "op_frac": r16["alg_bytes"] / ((r16["us_fwd"] + r16["us_stats"]) * 1e-6) / 1e9 / peak},
                 "method": "CUDA events around a CUDA graph of back-to-back launches cycling through buffer sets > L2"}
         except Exception as e:  # keep the headline even if the micro-bench fails
