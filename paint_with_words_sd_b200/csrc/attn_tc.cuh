@@ -25,25 +25,29 @@ template <int D>
 struct Cfg {
   static constexpr int NA = (D + 63) / 64;
   static constexpr int DP = (D + 15) / 16 * 16;
-  static constexpr int BN = (D <= 64) ? 128 : 64;          // keys per tile
+  static constexpr int BN = 64;                            // keys per tile
   static constexpr int NQ = (D <= 80) ? 2 : 1;             // query tiles per CTA
-  static constexpr int NK = (D <= 80) ? 3 : 2;             // K ring depth
-  static constexpr int NV = 2;                             // V ring depth
-  static constexpr int NPA = BN / 64;                      // 64-column atoms of a P tile
+  static constexpr int NK = (D <= 80) ? 4 : 3;             // K ring depth
+  static constexpr int NV = (D <= 80) ? 3 : 2;             // V ring depth
+  // Row sums ride on the P.V UMMA where the last V atom has a spare column (see xattn_tc.cuh): accumulator column D.
+  static constexpr bool ONES = (D == 40 || D == 80);
+  static constexpr int DPV = ONES ? (D + 16) / 16 * 16 : DP;   // UMMA N of P.V: 48, 64, 96, 160
   static constexpr uint32_t QATOM = 128 * 128, KATOM = BN * 128, PATOM = 128 * 128;
   static constexpr uint32_t QBYTES = NA * QATOM;           // one query tile
   static constexpr uint32_t KSTAGE = NA * KATOM, VSTAGE = NA * KATOM;
-  static constexpr uint32_t PBUF = NPA * PATOM;
+  static constexpr uint32_t PBUF = PATOM;                  // [128 x 64] fp16
   static constexpr uint32_t OFF_K = NQ * QBYTES;
   static constexpr uint32_t OFF_V = OFF_K + NK * KSTAGE;
   static constexpr uint32_t OFF_P = OFF_V + NV * VSTAGE;
   static constexpr uint32_t OFF_BAR = OFF_P + NQ * PBUF;
   static constexpr uint32_t SMEM = OFF_BAR + 256 + 1024;
   static constexpr int TMEM_COLS = 512;
-  static_assert(NQ * (BN + DP) <= 512, "TMEM budget");
+  static constexpr int OSTRIDE = (DPV + 31) / 32 * 32;
+  static_assert(NQ * 2 * BN + NQ * OSTRIDE <= 512, "TMEM budget");
   static_assert(SMEM <= 232448, "shared memory budget");
-  __host__ __device__ static constexpr uint32_t col_s(int g) { return g * BN; }
-  __host__ __device__ static constexpr uint32_t col_o(int g) { return NQ * BN + g * ((DP + 31) / 32 * 32); }
+  // S is double-buffered per query tile so the next S = Q K^T is issued while the softmax of the current one runs
+  __host__ __device__ static constexpr uint32_t col_s(int g, int buf) { return (g * 2 + buf) * BN; }
+  __host__ __device__ static constexpr uint32_t col_o(int g) { return NQ * 2 * BN + g * OSTRIDE; }
 };
 
 struct Params {
@@ -59,6 +63,7 @@ __device__ __forceinline__ void tmem_ld_row(uint32_t ta, float* v) {
   else if constexpr (N == 64) { ptx::tmem_ld64_sync(ta, v); }
   else if constexpr (N == 48) { ptx::tmem_ld32_sync(ta, v); ptx::tmem_ld16_sync(ta + 32, v + 32); }
   else if constexpr (N == 80) { ptx::tmem_ld64_sync(ta, v); ptx::tmem_ld16_sync(ta + 64, v + 64); }
+  else if constexpr (N == 96) { ptx::tmem_ld64_sync(ta, v); ptx::tmem_ld32_sync(ta + 64, v + 64); }
   else if constexpr (N == 160) { ptx::tmem_ld64_sync(ta, v); ptx::tmem_ld64_sync(ta + 64, v + 64); ptx::tmem_ld32_sync(ta + 128, v + 128); }
 }
 template <int N>
@@ -66,6 +71,7 @@ __device__ __forceinline__ void tmem_st_row(uint32_t ta, const float* v) {
   if constexpr (N == 64) { ptx::tmem_st64(ta, v); }
   else if constexpr (N == 48) { ptx::tmem_st32(ta, v); ptx::tmem_st16(ta + 32, v + 32); }
   else if constexpr (N == 80) { ptx::tmem_st64(ta, v); ptx::tmem_st16(ta + 64, v + 64); }
+  else if constexpr (N == 96) { ptx::tmem_st64(ta, v); ptx::tmem_st32(ta + 64, v + 64); }
   else if constexpr (N == 160) { ptx::tmem_st64(ta, v); ptx::tmem_st64(ta + 64, v + 64); ptx::tmem_st32(ta + 128, v + 128); }
   ptx::tmem_st_wait();
 }
@@ -80,8 +86,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
   unsigned char* smem_gen = smem_raw + (smem0 - ptx::smem_u32(smem_raw));
   const uint32_t bar0 = smem0 + C::OFF_BAR;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  constexpr int B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 4, B_VFULL = 7, B_VEMPTY = 9, B_SREADY = 11, B_PREADY = 13,
-                B_OREADY = 15, B_TMEMPTR = 17;
+  constexpr int B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 5, B_VFULL = 9, B_VEMPTY = 12, B_SREADY = 15, B_SFREE = 19,
+                B_PREADY = 23, B_OREADY = 25, B_TMEMPTR = 27;   // SREADY/SFREE are indexed [g*2 + buf]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // block -> (image, head, query super-tile)
   const int qtiles = (p.N + 128 * C::NQ - 1) / (128 * C::NQ);
@@ -100,8 +106,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     ptx::mbar_init(BAR(B_QFULL), 1);
     for (int s = 0; s < C::NK; ++s) { ptx::mbar_init(BAR(B_KFULL + s), 1); ptx::mbar_init(BAR(B_KEMPTY + s), 1); }
     for (int s = 0; s < C::NV; ++s) { ptx::mbar_init(BAR(B_VFULL + s), 1); ptx::mbar_init(BAR(B_VEMPTY + s), 1); }
+    for (int i = 0; i < 4; ++i) {
+      ptx::mbar_init(BAR(B_SREADY + i), 1);
+      ptx::mbar_init(BAR(B_SFREE + i), 4);
+    }
     for (int g = 0; g < 2; ++g) {
-      ptx::mbar_init(BAR(B_SREADY + g), 1);
       ptx::mbar_init(BAR(B_PREADY + g), 4);
       ptx::mbar_init(BAR(B_OREADY + g), 1);
     }
@@ -156,16 +165,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % C::NK;
         ptx::mbar_wait(BAR(B_KFULL + st), (uint32_t)((j / C::NK) & 1));
+        const int buf = j & 1;
         for (int g = 0; g < nq_live; ++g) {
-          if (j >= 1) ptx::mbar_wait(BAR(B_PREADY + g), (uint32_t)((j - 1) & 1));   // S_g of tile j-1 consumed
+          ptx::mbar_wait(BAR(B_SFREE + g * 2 + buf), (uint32_t)(((j >> 1) & 1) ^ 1));   // softmax done with this S buffer
           ptx::tc_fence_after();
           const uint32_t qb = smem0 + g * C::QBYTES, kb = smem0 + C::OFF_K + st * C::KSTAGE;
 #pragma unroll
           for (int ks = 0; ks < C::DP / 16; ++ks)
-            ptx::umma_ss(tmem_base + C::col_s(g),
+            ptx::umma_ss(tmem_base + C::col_s(g, buf),
                          ptx::make_sw128_desc(qb + (ks / 4) * C::QATOM + (ks % 4) * 32, 16, 1024),
                          ptx::make_sw128_desc(kb + (ks / 4) * C::KATOM + (ks % 4) * 32, 16, 1024), idesc, ks > 0);
-          ptx::umma_commit(BAR(B_SREADY + g));
+          ptx::umma_commit(BAR(B_SREADY + g * 2 + buf));
         }
         ptx::umma_commit(BAR(B_KEMPTY + st));
       }
@@ -174,7 +184,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
   } else if (warp == 3) {
     // ------------------------------------------------ UMMA issuer: O_g += P_g V_j
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_f16(128, C::DP, false, true);
+      constexpr uint32_t idesc = ptx::make_idesc_f16(128, C::DPV, false, true);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % C::NV;
         ptx::mbar_wait(BAR(B_VFULL + st), (uint32_t)((j / C::NV) & 1));
@@ -203,27 +213,27 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       unsigned char* prow = smem_gen + C::OFF_P + g * C::PBUF + (row >> 3) * 1024 + (row & 7) * 128;
       float m_run = -INFINITY, l_run = 0.f;
       for (int j = 0; j < n_kv; ++j) {
-        ptx::mbar_wait(BAR(B_SREADY + g), (uint32_t)(j & 1));
+        const int buf = j & 1;
+        ptx::mbar_wait(BAR(B_SREADY + g * 2 + buf), (uint32_t)((j >> 1) & 1));
         ptx::tc_fence_after();
-        const uint32_t ts = tmem_base + lane_addr + C::col_s(g);
+        const uint32_t ts = tmem_base + lane_addr + C::col_s(g, buf);
         const int valid = p.N - j * C::BN;          // keys of this tile that exist (>= BN except in the last tile)
         // pass 1 over S (TMEM reads are cheap): row max of the tile
-        float m_tile = -INFINITY;
-#pragma unroll
-        for (int c0 = 0; c0 < C::BN; c0 += 64) {
+        float m_tile;
+        {
           float s[64];
-          ptx::tmem_ld64_sync(ts + c0, s);
+          ptx::tmem_ld64_sync(ts, s);
           if (valid < C::BN) {
 #pragma unroll
             for (int c = 0; c < 64; ++c)
-              if (c0 + c >= valid) s[c] = -INFINITY;
+              if (c >= valid) s[c] = -INFINITY;
           }
           float m0 = s[0], m1 = s[1], m2 = s[2], m3 = s[3];
 #pragma unroll
           for (int c = 4; c < 64; c += 4) {
             m0 = fmaxf(m0, s[c]); m1 = fmaxf(m1, s[c + 1]); m2 = fmaxf(m2, s[c + 2]); m3 = fmaxf(m3, s[c + 3]);
           }
-          m_tile = fmaxf(m_tile, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+          m_tile = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
         }
         // lazy rescale: move the reference max only when the tile exceeds it by more than 2^8
         const bool need = (j == 0) || ((m_tile - m_run) * sl2 > 8.0f);
@@ -237,11 +247,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         if (j >= 1) ptx::mbar_wait(BAR(B_OREADY + g), (uint32_t)((j - 1) & 1));
         if (j >= 1 && __any_sync(0xffffffffu, need)) {
           ptx::tc_fence_after();
-          float o[C::DP];
-          tmem_ld_row<C::DP>(tmem_base + lane_addr + C::col_o(g), o);
+          float o[C::DPV];
+          tmem_ld_row<C::DPV>(tmem_base + lane_addr + C::col_o(g), o);
 #pragma unroll
-          for (int c = 0; c < C::DP; ++c) o[c] *= factor;
-          tmem_st_row<C::DP>(tmem_base + lane_addr + C::col_o(g), o);
+          for (int c = 0; c < C::DPV; ++c) o[c] *= factor;
+          tmem_st_row<C::DPV>(tmem_base + lane_addr + C::col_o(g), o);
         }
         // pass 2: p = 2^((s - m) * scale * log2 e) -> fp16 -> swizzled P tile, 32 columns at a time
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -249,6 +259,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         for (int c0 = 0; c0 < C::BN; c0 += 32) {
           float s[32];
           ptx::tmem_ld32_sync(ts + c0, s);
+          if (c0 + 32 == C::BN) {                   // last read of this S buffer: hand it back to the S-UMMA issuer
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(BAR(B_SFREE + g * 2 + buf));
+          }
           if (valid < C::BN) {
 #pragma unroll
             for (int c = 0; c < 32; ++c)
@@ -259,7 +274,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
           for (int c = 0; c < 32; c += 4) {
             const float e0 = ptx::ex2(fmaf(s[c], sl2, nm)), e1 = ptx::ex2(fmaf(s[c + 1], sl2, nm));
             const float e2 = ptx::ex2(fmaf(s[c + 2], sl2, nm)), e3 = ptx::ex2(fmaf(s[c + 3], sl2, nm));
-            a0 += e0; a1 += e1; a2 += e2; a3 += e3;
+            if constexpr (!C::ONES) { a0 += e0; a1 += e1; a2 += e2; a3 += e3; }
             const __half2 h01 = __floats2half2_rn(e0, e1), h23 = __floats2half2_rn(e2, e3);
             pk[c / 2] = *reinterpret_cast<const uint32_t*>(&h01);
             pk[c / 2 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
@@ -267,11 +282,22 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int c = c0 / 8 + q;               // 16-byte chunk index within the row
-            *reinterpret_cast<uint4*>(prow + (c >> 3) * C::PATOM + (((c & 7) ^ (row & 7)) << 4)) =
+            *reinterpret_cast<uint4*>(prow + (((c & 7) ^ (row & 7)) << 4)) =
                 make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
           }
         }
-        l_run = l_run * factor + ((a0 + a1) + (a2 + a3));
+        if constexpr (C::ONES) {
+          // key r = this thread's row index: V[r][D] = 1.0 in the last V atom -> accumulator column D = row sum of P
+          ptx::mbar_wait(BAR(B_VFULL + j % C::NV), (uint32_t)((j / C::NV) & 1));
+          if (row < C::BN && row < valid) {
+            unsigned char* vlast = smem_gen + C::OFF_V + (j % C::NV) * C::VSTAGE + (C::NA - 1) * C::KATOM;
+            constexpr int cc = D % 64;
+            *reinterpret_cast<__half*>(vlast + row * 128 + ((((cc >> 3) ^ (row & 7))) << 4) + (cc & 7) * 2) =
+                __float2half(1.0f);
+          }
+        } else {
+          l_run = l_run * factor + ((a0 + a1) + (a2 + a3));
+        }
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
         __syncwarp();
@@ -280,9 +306,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       // epilogue: O / l -> fp16 -> global
       ptx::mbar_wait(BAR(B_OREADY + g), (uint32_t)((n_kv - 1) & 1));
       ptx::tc_fence_after();
-      float o[C::DP];
-      tmem_ld_row<C::DP>(tmem_base + lane_addr + C::col_o(g), o);
-      const float inv = 1.f / l_run;
+      float o[C::DPV];
+      tmem_ld_row<C::DPV>(tmem_base + lane_addr + C::col_o(g), o);
+      const float inv = 1.f / (C::ONES ? o[D] : l_run);
       const int n = row0 + g * 128 + row;
       if (n < p.N) {
         __half* orow = p.out + (int64_t)b * p.o_bs + (int64_t)n * p.o_rs + h * D;
