@@ -11,7 +11,7 @@
 
 namespace {
 
-thread_local char g_last_cuda_error[256] = "";
+thread_local char g_last_cuda_error[640] = "";
 
 int cuda_fail(cudaError_t e);
 

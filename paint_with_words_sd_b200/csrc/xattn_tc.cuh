@@ -82,7 +82,6 @@ struct TcParams {
   int units;        // B * tiles * H
   int k_batched;    // 0 when k/v have batch stride 0 (shared context)
   long long* timeline;   // debug only (see PWW_TL)
-  int stagger;           // cycles softmax group 1 holds back its first tile (de-synchronises the two groups)
 };
 
 __device__ __forceinline__ void tl_init(const TcParams& tp) {
@@ -94,17 +93,6 @@ __device__ __forceinline__ void tl_dump(const TcParams& tp) {   // call after a 
     for (int i = threadIdx.x; i < kTlTags * kTlIts; i += blockDim.x) tp.timeline[i] = tl_buf[i];
 }
 
-struct Unit {
-  int b, tile, h;
-};
-__device__ __forceinline__ Unit decode_unit(int u, int tiles, int H) {
-  Unit r;
-  r.h = u % H;
-  int t = u / H;
-  r.tile = t % tiles;
-  r.b = t / tiles;
-  return r;
-}
 // Walks consecutive units without a div/mod per step.
 struct UnitIter {
   int b, tile, h, tiles, H;
@@ -348,10 +336,6 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         const int widx = s_widx[ui.b];
         const float coef = s_coef[ui.b];
         ptx::mbar_wait(BAR(B_SREADY + g), (uint32_t)(local & 1));
-        if (it == 1 && tp.stagger > 0) {          // group 1 starts half a period late; the offset then persists
-          const long long t0 = clock64();
-          while (clock64() - t0 < tp.stagger) {}
-        }
         if ((threadIdx.x & 127) == 64) PWW_TL(5, it);
         ptx::tc_fence_after();
         float s[kTP];
@@ -385,17 +369,18 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         }
         const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
         const float nm = -mx * sl2;
-        // p_j = 2^(t_j*sl2 - mx*sl2), UNNORMALISED fp16; O is scaled by 1/rowsum in the epilogue (fp32).
-        // Two exponentials per MUFU op (ex2.approx.f16x2): the argument is <= 0 and P is stored as fp16 anyway.
+        // p_j = 2^(t_j*sl2 - mx*sl2), UNNORMALISED, packed to fp16; O is scaled by 1/rowsum in the epilogue (fp32).
+        // (ex2.approx.f16x2 was tried: on sm_100a it lowers to two MUFU.EX2.F16 plus a PRMT -- no MUFU saving and
+        //  40 extra instructions per row -- so the exponentials stay fp32.)
         float a0 = 0.f, a1 = 0.f;
         uint32_t pk[kTP / 2];
 #pragma unroll
         for (int j = 0; j < kTP; j += 2) {
-          const __half2 arg = __floats2half2_rn(fmaf(s[j], sl2, nm), fmaf(s[j + 1], sl2, nm));
-          const uint32_t e = ptx::ex2_f16x2(*reinterpret_cast<const uint32_t*>(&arg));
-          pk[j / 2] = e;
+          const float e0 = ptx::ex2(fmaf(s[j], sl2, nm)), e1 = ptx::ex2(fmaf(s[j + 1], sl2, nm));
+          const __half2 h = __floats2half2_rn(e0, e1);
+          pk[j / 2] = *reinterpret_cast<const uint32_t*>(&h);
           if constexpr (!C::ONES) {
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&e));
+            const float2 f = __half22float2(h);       // sum exactly what the UMMA will multiply
             a0 += f.x; a1 += f.y;
           }
         }
@@ -747,14 +732,6 @@ inline int num_sms() {
 
 inline int stats_grid(int units) { return units < num_sms() ? units : num_sms(); }
 
-inline int debug_stagger() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("PWW_STAGGER");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
-}
 inline long long*& debug_timeline() {
   static long long* ptr = nullptr;
   return ptr;
@@ -775,7 +752,6 @@ cudaError_t launch_fwd(const XattnParams& x, cudaStream_t s) {
   tp.units = x.B * tp.tiles * x.H;
   tp.k_batched = x.k_bs > 0 ? 1 : 0;
   tp.timeline = debug_timeline();
-  tp.stagger = debug_stagger();
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(xattn_fwd_tc_kernel<D, 77>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
@@ -806,7 +782,6 @@ cudaError_t launch_stats(const XattnParams& x, cudaStream_t s) {
   tp.units = x.B * tp.tiles * x.H;
   tp.k_batched = x.k_bs > 0 ? 1 : 0;
   tp.timeline = debug_timeline();
-  tp.stagger = debug_stagger();
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(xattn_stats_tc_kernel<D, 77>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::S_SMEM);
