@@ -109,6 +109,24 @@ struct UnitIter {
     }
   }
 };
+// Forward-kernel unit order: tile-major, image-minor, head-minor.  Consecutive (image, tile) groups alternate between
+// images, so every CTA's contiguous range mixes biased (mask + bias work) and unbiased units instead of some CTAs
+// getting only the expensive kind (the b-major order left ~10 % of the kernel as tail imbalance).
+struct UnitIterTM {
+  int b, tile, h, B, H;
+  __device__ __forceinline__ UnitIterTM(int u, int B_, int H_) : B(B_), H(H_) {
+    h = u % H_;
+    const int t = u / H_;
+    b = t % B_;
+    tile = t / B_;
+  }
+  __device__ __forceinline__ void next() {
+    if (++h == H) {
+      h = 0;
+      if (++b == B) { b = 0; ++tile; }
+    }
+  }
+};
 __device__ __forceinline__ void cta_range(int units, int& u0, int& u1) {
   u0 = (int)((long long)blockIdx.x * units / gridDim.x);
   u1 = (int)((long long)(blockIdx.x + 1) * units / gridDim.x);
@@ -181,7 +199,7 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   if (warp == 0) {
     // ===================================== TMA producer: Q and K tiles =====================================
     if (lane == 0) {
-      UnitIter uq(u0, tp.tiles, p.H);
+      UnitIterTM uq(u0, p.B, p.H);
       for (int it = 0; it < n_it; ++it, uq.next()) {
         const int st = it % C::NQK;
         ptx::mbar_wait(BAR(B_QEMPTY + st), (uint32_t)(((it / C::NQK) & 1) ^ 1));
@@ -199,7 +217,7 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     __syncwarp();
   } else if (warp == 10) {
     // ===================================== TMA producer: mask tiles and V tiles =====================================
-    UnitIter uv(u0, tp.tiles, p.H);
+    UnitIterTM uv(u0, p.B, p.H);
     int grp = -1;
     for (int it = 0; it < n_it; ++it, uv.next()) {
       if (it == 0 || uv.h == 0) {                 // first unit of an (image, tile) group: stage its mask tile
@@ -294,7 +312,7 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     const float sl2 = p.scale * 1.4426950408889634f;
     const float* mask_row = reinterpret_cast<const float*>(smem_gen + C::OFF_MASK) + row * (TT ? TT : p.T);
     unsigned char* prow = smem_gen + C::OFF_P + g * kPBuf + (row >> 3) * 1024 + (row & 7) * 128;
-    UnitIter ui(u0, tp.tiles, p.H);
+    UnitIterTM ui(u0, p.B, p.H);
     int grp = -1;
     // deferred epilogue state: iteration `pend` of this group has its P.V in flight / finished
     int pend_local = -1, pend_n = 0;
