@@ -134,6 +134,7 @@ class PwWSampler:
         self.extra_input = extra_input            # inpaint: [m,5,h,w] (mask + masked-image latents)
         self.use_graph = use_graph and latents.is_cuda
         self._graph = None
+        self._kv_graph = None
         self.native_launches_per_step = None
         self._probed = probe_weight_function(weight_function, 1.0)
         self._ctx = self._merge_contexts(cond_ctxs, uncond_ctxs)
@@ -221,8 +222,21 @@ class PwWSampler:
         for k, h in pinned.items():
             dev[k].copy_(h, non_blocking=True)
             n += h.numel() * h.element_size()
-        if "CONTEXT_TENSOR" in pinned:
-            _attention.refresh_kv_cache(self._ctx)     # the cached K/V follow the new context
+        if "CONTEXT_TENSOR" in pinned and self._ctx.get("KV_CACHE"):
+            # the cached K/V follow the new context: 16 small GEMMs, replayed as one CUDA graph
+            if not self.use_graph:
+                _attention.refresh_kv_cache(self._ctx)
+            else:
+                if self._kv_graph is None:
+                    s = torch.cuda.Stream(device=self.device)
+                    s.wait_stream(torch.cuda.current_stream(self.device))
+                    with torch.cuda.stream(s):
+                        _attention.refresh_kv_cache(self._ctx)
+                    torch.cuda.current_stream(self.device).wait_stream(s)
+                    self._kv_graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self._kv_graph):
+                        _attention.refresh_kv_cache(self._ctx)
+                self._kv_graph.replay()
         return n
 
     def restart(self, latents: Optional[torch.Tensor] = None):
