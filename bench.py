@@ -184,7 +184,7 @@ def run_reference_arm(args, rank: int):
                                        f"{r['seconds']:.1f} s; bounded to ~150 s"},
             "e2e": {"value": r["steps_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -256,7 +256,29 @@ def xattn_roofline(device, B: int, biased: int, N=4096, H=8, D=40, T=77, target_
 # ------------------------------------------------------------------------------------------------
 # main arm
 # ------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: route everything else written to fd 1 (NCCL's version banner, library
+    chatter) to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=27)
@@ -346,8 +368,8 @@ def main():
 
         if args.quick:
             if rank == 0:
-                print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms / args.steps,
-                                  "steps": args.steps, "quick": True}), flush=True)
+                emit({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms / args.steps,
+                      "steps": args.steps, "quick": True})
             return
         # ---- e2e: host buffers in, host buffer out, every step ----
         dev_in = sampler.device_inputs()
@@ -413,7 +435,7 @@ def main():
             except Exception as e:
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                         "sample": "failed: " + repr(e)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -35,9 +35,12 @@ constexpr uint32_t kMaskBytes = kBM * kTP * 4;
 constexpr int kTmemCols = 512;
 constexpr int kMaxBatch = 256;   // images per launch (the C ABI splits larger batches)
 constexpr int kMaxLocal = 4;     // images one CTA's unit range can touch: B/148 + 2 <= 4 for B <= 256
-// TMEM column map (512 columns): S buffers 80 wide, O buffers up to 160 wide
-__host__ __device__ constexpr uint32_t col_s(int g) { return g ? 96u : 0u; }
-__host__ __device__ constexpr uint32_t col_o(int g) { return g ? 352u : 192u; }
+// TMEM column map (512 columns): S buffers 80 fp32 columns, P buffers 40 columns (80 packed fp16: the A operand of
+// the P.V UMMA is read straight from tensor memory), O buffers up to 160 columns.  For D = 160 there is no room for
+// separate P buffers: P aliases the first 40 columns of its S buffer.
+template <int D> __host__ __device__ constexpr uint32_t col_s(int g) { return g ? 96u : 0u; }
+template <int D> __host__ __device__ constexpr uint32_t col_p(int g) { return D == 160 ? (g ? 96u : 0u) : (g ? 232u : 192u); }
+template <int D> __host__ __device__ constexpr uint32_t col_o(int g) { return D == 160 ? (g ? 352u : 192u) : (g ? 384u : 288u); }
 
 template <int D>
 struct Cfg {
@@ -46,8 +49,8 @@ struct Cfg {
   static constexpr int KSTEPS = DP / 16;
   // Q/K tiles and V tiles live in separate rings: Q/K of a unit are released as soon as S = Q K^T is done (long
   // before P.V), so the next units' Q/K loads -- ~2 us of TMA latency for 200+ short rows -- are issued early.
-  static constexpr int NQK = (D <= 64) ? 3 : 1;
-  static constexpr int NV = (D <= 64) ? 2 : 1;
+  static constexpr int NQK = (D <= 64) ? 4 : (D <= 80 ? 2 : 1);
+  static constexpr int NV = (D <= 64) ? 3 : 2;
   static constexpr uint32_t QKSTAGE = NA * (kQAtom + kKAtom);
   static constexpr uint32_t VSTAGE = NA * kKAtom;
   // Row sums ride on the P.V UMMA: when the last 64-column V atom has a spare column (D = 40, 80) that column is
@@ -56,8 +59,8 @@ struct Cfg {
   static constexpr bool ONES = (D == 40 || D == 80);
   static constexpr int DPV = ONES ? (D + 16) / 16 * 16 : DP;   // UMMA N of P.V: 48, 64, 96, 160
   static constexpr uint32_t OFF_V = NQK * QKSTAGE;
-  static constexpr uint32_t OFF_P = OFF_V + NV * VSTAGE;
-  static constexpr uint32_t OFF_MASK = OFF_P + 2 * kPBuf;
+  static constexpr uint32_t OFF_MASK = OFF_V + NV * VSTAGE;
+  static constexpr bool P_ALIAS = (D == 160);      // P overwrites S: the next S = Q K^T must wait for P.V, not for P
   static constexpr uint32_t OFF_BAR = OFF_MASK + kMaskBytes;
   static constexpr uint32_t SMEM = OFF_BAR + 256 + 1024;   // + alignment slack
   // stats kernel: Q and K only
@@ -152,8 +155,8 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   const uint32_t bar0 = smem0 + C::OFF_BAR;
   // barrier slots (8 bytes each)
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  constexpr int B_QFULL = 0, B_QEMPTY = 3, B_VFULL = 6, B_VEMPTY = 8, B_MFULL = 10, B_MEMPTY = 11, B_SREADY = 12,
-                B_PREADY = 14, B_OREADY = 16, B_OFREE = 18, B_TMEMPTR = 20;
+  constexpr int B_QFULL = 0, B_QEMPTY = 4, B_VFULL = 8, B_VEMPTY = 11, B_MFULL = 14, B_MEMPTY = 15, B_SREADY = 16,
+                B_PREADY = 18, B_OREADY = 20, B_OFREE = 22, B_TMEMPTR = 24;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int u0, u1;
   cta_range(tp.units, u0, u1);
@@ -261,7 +264,8 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       for (int it = 0; it < n_it; ++it) {
         const int st = it % C::NQK, g = it & 1, local = it >> 1;
         ptx::mbar_wait(BAR(B_QFULL + st), (uint32_t)((it / C::NQK) & 1));
-        if (local >= 1) ptx::mbar_wait(BAR(B_PREADY + g), (uint32_t)((local - 1) & 1));   // S[g] consumed
+        if (local >= 1)                                  // S[g] consumed (and, when P aliases S, P.V done with it)
+          ptx::mbar_wait(BAR((C::P_ALIAS ? B_OREADY : B_PREADY) + g), (uint32_t)((local - 1) & 1));
         PWW_TL(2, it);
         ptx::tc_fence_after();
         const uint32_t sb = smem0 + st * C::QKSTAGE;
@@ -269,7 +273,7 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         for (int ks = 0; ks < C::KSTEPS; ++ks) {
           const uint32_t qa = sb + (ks / 4) * kQAtom + (ks % 4) * 32;
           const uint32_t ka = sb + C::NA * kQAtom + (ks / 4) * kKAtom + (ks % 4) * 32;
-          ptx::umma_ss(tmem_base + col_s(g), ptx::make_sw128_desc(qa, 16, 1024), ptx::make_sw128_desc(ka, 16, 1024),
+          ptx::umma_ss(tmem_base + col_s<D>(g), ptx::make_sw128_desc(qa, 16, 1024), ptx::make_sw128_desc(ka, 16, 1024),
                        idesc_qk, ks > 0);
         }
         ptx::umma_commit(BAR(B_SREADY + g));
@@ -290,14 +294,10 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         PWW_TL(3, j);
         ptx::tc_fence_after();
         const uint32_t vb = smem0 + C::OFF_V + st * C::VSTAGE;
-        const uint32_t pb = smem0 + C::OFF_P + g * kPBuf;
 #pragma unroll
-        for (int ks = 0; ks < kTP / 16; ++ks) {
-          const uint32_t pa = pb + (ks / 4) * kPAtom + (ks % 4) * 32;
-          const uint32_t va = vb + ks * 16 * 128;
-          ptx::umma_ss(tmem_base + col_o(g), ptx::make_sw128_desc(pa, 16, 1024),
-                       ptx::make_sw128_desc(va, kKAtom, 1024), idesc_pv, ks > 0);
-        }
+        for (int ks = 0; ks < kTP / 16; ++ks)          // A = P from tensor memory: 8 columns (16 fp16) per k-step
+          ptx::umma_ts(tmem_base + col_o<D>(g), tmem_base + col_p<D>(g) + ks * 8,
+                       ptx::make_sw128_desc(vb + ks * 16 * 128, kKAtom, 1024), idesc_pv, ks > 0);
         ptx::umma_commit(BAR(B_OREADY + g));
         ptx::umma_commit(BAR(B_VEMPTY + st));
         PWW_TL(8, j);
@@ -311,7 +311,6 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     const uint32_t lane_addr = (uint32_t)((warp & 3) << 5) << 16;
     const float sl2 = p.scale * 1.4426950408889634f;
     const float* mask_row = reinterpret_cast<const float*>(smem_gen + C::OFF_MASK) + row * (TT ? TT : p.T);
-    unsigned char* prow = smem_gen + C::OFF_P + g * kPBuf + (row >> 3) * 1024 + (row & 7) * 128;
     UnitIterTM ui(u0, p.B, p.H);
     int grp = -1;
     // deferred epilogue state: iteration `pend` of this group has its P.V in flight / finished
@@ -325,7 +324,7 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     };
     auto epilogue = [&]() {                      // O[g] (fp32, TMEM) -> * 1/rowsum -> fp16 -> global
       ptx::tc_fence_after();
-      const uint32_t ta = tmem_base + lane_addr + col_o(g);
+      const uint32_t ta = tmem_base + lane_addr + col_o<D>(g);
       float o[C::DPV];
       // whole accumulator row in as few TMEM loads as possible
       if constexpr (C::DPV == 48) { ptx::tmem_ld32_sync(ta, o); ptx::tmem_ld16_sync(ta + 32, o + 32); }
@@ -357,8 +356,8 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         if ((threadIdx.x & 127) == 64) PWW_TL(5, it);
         ptx::tc_fence_after();
         float s[kTP];
-        ptx::tmem_ld64_sync(tmem_base + lane_addr + col_s(g), s);
-        ptx::tmem_ld16_sync(tmem_base + lane_addr + col_s(g) + 64, s + 64);
+        ptx::tmem_ld64_sync(tmem_base + lane_addr + col_s<D>(g), s);
+        ptx::tmem_ld16_sync(tmem_base + lane_addr + col_s<D>(g) + 64, s + 64);
         if ((threadIdx.x & 127) == 64) PWW_TL(0, it);
         // logits t_j = S_j + coef*w_j (unscaled), row max with 4 independent chains
         if (widx >= 0) {
@@ -416,10 +415,9 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         // the previous iteration's P.V must be done before its P buffer is overwritten
         if (lane == 0) { const int qd = warp & 3; PWW_TL((qd == 2 ? 7 : (qd == 3 ? 9 : (qd == 0 ? 10 : 11))), it); }
         if (pend_local >= 0) ptx::mbar_wait(BAR(B_OREADY + g), (uint32_t)(pend_local & 1));
-#pragma unroll
-        for (int c = 0; c < kTP / 8; ++c)
-          *reinterpret_cast<uint4*>(prow + (c >> 3) * kPAtom + (((c & 7) ^ (row & 7)) << 4)) =
-              make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        ptx::tmem_st32_u32(tmem_base + lane_addr + col_p<D>(g), pk);          // P row -> tensor memory (packed fp16)
+        ptx::tmem_st8_u32(tmem_base + lane_addr + col_p<D>(g) + 32, pk + 32);
+        ptx::tmem_st_wait();
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
         warp_arrive(BAR(B_PREADY + g));
