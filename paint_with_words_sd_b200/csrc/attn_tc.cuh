@@ -35,19 +35,19 @@ struct Cfg {
   static constexpr uint32_t QATOM = 128 * 128, KATOM = BN * 128, PATOM = 128 * 128;
   static constexpr uint32_t QBYTES = NA * QATOM;           // one query tile
   static constexpr uint32_t KSTAGE = NA * KATOM, VSTAGE = NA * KATOM;
-  static constexpr uint32_t PBUF = PATOM;                  // [128 x 64] fp16
   static constexpr uint32_t OFF_K = NQ * QBYTES;
   static constexpr uint32_t OFF_V = OFF_K + NK * KSTAGE;
-  static constexpr uint32_t OFF_P = OFF_V + NV * VSTAGE;
-  static constexpr uint32_t OFF_BAR = OFF_P + NQ * PBUF;
+  static constexpr uint32_t OFF_BAR = OFF_V + NV * VSTAGE;
   static constexpr uint32_t SMEM = OFF_BAR + 256 + 1024;
   static constexpr int TMEM_COLS = 512;
   static constexpr int OSTRIDE = (DPV + 31) / 32 * 32;
-  static_assert(NQ * 2 * BN + NQ * OSTRIDE <= 512, "TMEM budget");
+  static_assert(NQ * 2 * BN + NQ * 32 + NQ * OSTRIDE <= 512, "TMEM budget");
   static_assert(SMEM <= 232448, "shared memory budget");
   // S is double-buffered per query tile so the next S = Q K^T is issued while the softmax of the current one runs
   __host__ __device__ static constexpr uint32_t col_s(int g, int buf) { return (g * 2 + buf) * BN; }
-  __host__ __device__ static constexpr uint32_t col_o(int g) { return NQ * 2 * BN + g * OSTRIDE; }
+  // P (64 fp16 per row = 32 columns) is the A operand of the P.V UMMA, read straight from tensor memory
+  __host__ __device__ static constexpr uint32_t col_p(int g) { return NQ * 2 * BN + g * 32; }
+  __host__ __device__ static constexpr uint32_t col_o(int g) { return NQ * 2 * BN + NQ * 32 + g * OSTRIDE; }
 };
 
 struct Params {
@@ -191,11 +191,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         for (int g = 0; g < nq_live; ++g) {
           ptx::mbar_wait(BAR(B_PREADY + g), (uint32_t)(j & 1));
           ptx::tc_fence_after();
-          const uint32_t pb = smem0 + C::OFF_P + g * C::PBUF, vb = smem0 + C::OFF_V + st * C::VSTAGE;
+          const uint32_t vb = smem0 + C::OFF_V + st * C::VSTAGE;
 #pragma unroll
           for (int ks = 0; ks < C::BN / 16; ++ks)
-            ptx::umma_ss(tmem_base + C::col_o(g),
-                         ptx::make_sw128_desc(pb + (ks / 4) * C::PATOM + (ks % 4) * 32, 16, 1024),
+            ptx::umma_ts(tmem_base + C::col_o(g), tmem_base + C::col_p(g) + ks * 8,
                          ptx::make_sw128_desc(vb + ks * 16 * 128, C::KATOM, 1024), idesc, (j > 0) || (ks > 0));
           ptx::umma_commit(BAR(B_OREADY + g));
         }
@@ -210,7 +209,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       const int row = ((warp & 3) << 5) | lane;
       const uint32_t lane_addr = (uint32_t)((warp & 3) << 5) << 16;
       const float sl2 = p.scale * 1.4426950408889634f;
-      unsigned char* prow = smem_gen + C::OFF_P + g * C::PBUF + (row >> 3) * 1024 + (row & 7) * 128;
       float m_run = -INFINITY, l_run = 0.f;
       for (int j = 0; j < n_kv; ++j) {
         const int buf = j & 1;
@@ -279,13 +277,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
             pk[c / 2] = *reinterpret_cast<const uint32_t*>(&h01);
             pk[c / 2 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
           }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int c = c0 / 8 + q;               // 16-byte chunk index within the row
-            *reinterpret_cast<uint4*>(prow + (((c & 7) ^ (row & 7)) << 4)) =
-                make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-          }
+          ptx::tmem_st16_u32(tmem_base + lane_addr + C::col_p(g) + c0 / 2, pk);   // 32 fp16 = 16 columns of P
         }
+        ptx::tmem_st_wait();
         if constexpr (C::ONES) {
           // key r = this thread's row index: V[r][D] = 1.0 in the last V atom -> accumulator column D = row sum of P
           ptx::mbar_wait(BAR(B_VFULL + j % C::NV), (uint32_t)((j / C::NV) & 1));
