@@ -41,13 +41,15 @@ struct Cfg {
   static constexpr uint32_t SMEM = OFF_BAR + 256 + 1024;
   static constexpr int TMEM_COLS = 512;
   static constexpr int OSTRIDE = (DPV + 31) / 32 * 32;
-  static_assert(NQ * 2 * BN + NQ * 32 + NQ * OSTRIDE <= 512, "TMEM budget");
+  static constexpr int NP = (D == 80) ? 1 : 2;             // P buffers per query tile (TMEM is full at D = 80)
+  static_assert(NQ * 2 * BN + NQ * NP * 32 + NQ * OSTRIDE <= 512, "TMEM budget");
   static_assert(SMEM <= 232448, "shared memory budget");
   // S is double-buffered per query tile so the next S = Q K^T is issued while the softmax of the current one runs
   __host__ __device__ static constexpr uint32_t col_s(int g, int buf) { return (g * 2 + buf) * BN; }
   // P (64 fp16 per row = 32 columns) is the A operand of the P.V UMMA, read straight from tensor memory
-  __host__ __device__ static constexpr uint32_t col_p(int g) { return NQ * 2 * BN + g * 32; }
-  __host__ __device__ static constexpr uint32_t col_o(int g) { return NQ * 2 * BN + NQ * 32 + g * OSTRIDE; }
+  // double-buffered where TMEM allows, so the softmax of tile j+1 never waits for the P.V of tile j
+  __host__ __device__ static constexpr uint32_t col_p(int g, int buf) { return NQ * 2 * BN + (g * NP + buf) * 32; }
+  __host__ __device__ static constexpr uint32_t col_o(int g) { return NQ * 2 * BN + NQ * NP * 32 + g * OSTRIDE; }
 };
 
 struct Params {
@@ -87,7 +89,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
   const uint32_t bar0 = smem0 + C::OFF_BAR;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   constexpr int B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 5, B_VFULL = 9, B_VEMPTY = 12, B_SREADY = 15, B_SFREE = 19,
-                B_PREADY = 23, B_OREADY = 25, B_TMEMPTR = 27;   // SREADY/SFREE are indexed [g*2 + buf]
+                B_PREADY = 23, B_OREADY = 25, B_PFREE = 27, B_TMEMPTR = 31;   // SREADY/SFREE/PFREE: [g*2 + buf]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // block -> (image, head, query super-tile)
   const int qtiles = (p.N + 128 * C::NQ - 1) / (128 * C::NQ);
@@ -109,6 +111,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     for (int i = 0; i < 4; ++i) {
       ptx::mbar_init(BAR(B_SREADY + i), 1);
       ptx::mbar_init(BAR(B_SFREE + i), 4);
+      ptx::mbar_init(BAR(B_PFREE + i), 1);
     }
     for (int g = 0; g < 2; ++g) {
       ptx::mbar_init(BAR(B_PREADY + g), 4);
@@ -194,9 +197,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
           const uint32_t vb = smem0 + C::OFF_V + st * C::VSTAGE;
 #pragma unroll
           for (int ks = 0; ks < C::BN / 16; ++ks)
-            ptx::umma_ts(tmem_base + C::col_o(g), tmem_base + C::col_p(g) + ks * 8,
+            ptx::umma_ts(tmem_base + C::col_o(g), tmem_base + C::col_p(g, j % C::NP) + ks * 8,
                          ptx::make_sw128_desc(vb + ks * 16 * 128, C::KATOM, 1024), idesc, (j > 0) || (ks > 0));
           ptx::umma_commit(BAR(B_OREADY + g));
+          ptx::umma_commit(BAR(B_PFREE + g * 2 + j % C::NP));
         }
         ptx::umma_commit(BAR(B_VEMPTY + st));
       }
@@ -241,9 +245,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
           m_run = m_tile;
         }
         const float nm = -m_run * sl2;
-        // P.V of the previous tile must be complete before O is rescaled or P is overwritten
-        if (j >= 1) ptx::mbar_wait(BAR(B_OREADY + g), (uint32_t)((j - 1) & 1));
+        // this tile's P buffer must have been consumed by its previous P.V ...
+        const int pbuf = j % C::NP;
+        ptx::mbar_wait(BAR(B_PFREE + g * 2 + pbuf), (uint32_t)(((j / C::NP) & 1) ^ 1));
+        // ... and O may only be rescaled once the P.V of the previous tile has landed (rare path)
         if (j >= 1 && __any_sync(0xffffffffu, need)) {
+          ptx::mbar_wait(BAR(B_OREADY + g), (uint32_t)((j - 1) & 1));
           ptx::tc_fence_after();
           float o[C::DPV];
           tmem_ld_row<C::DPV>(tmem_base + lane_addr + C::col_o(g), o);
@@ -277,7 +284,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
             pk[c / 2] = *reinterpret_cast<const uint32_t*>(&h01);
             pk[c / 2 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
           }
-          ptx::tmem_st16_u32(tmem_base + lane_addr + C::col_p(g) + c0 / 2, pk);   // 32 fp16 = 16 columns of P
+          ptx::tmem_st16_u32(tmem_base + lane_addr + C::col_p(g, pbuf) + c0 / 2, pk);   // 32 fp16 = 16 columns of P
         }
         ptx::tmem_st_wait();
         if constexpr (C::ONES) {
