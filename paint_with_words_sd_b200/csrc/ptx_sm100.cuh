@@ -1,6 +1,6 @@
 // Thin inline-PTX wrappers for the sm_100a features the kernels use: mbarrier, TMA (cp.async.bulk[.tensor]),
 // tcgen05 (TMEM alloc, UMMA, commit, ld), proxy fences.  Every spin is bounded: a barrier that does not
-// complete within ~2 s traps (kernel error) instead of hanging the GPU.
+// complete within ~10 s traps (kernel error) instead of hanging the GPU.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -52,12 +52,12 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Wait for the phase with the given parity to complete.  Bounded: traps after ~2 s.
+// Wait for the phase with the given parity to complete.  Bounded: traps after ~10 s (long enough for instrumented profiler replays).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
+    if (clock64() - t0 > 20000000000LL) {
       printf("pww: mbarrier timeout block %d thread %d bar 0x%x parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
       __trap();
     }
