@@ -89,7 +89,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
   const uint32_t bar0 = smem0 + C::OFF_BAR;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   constexpr int B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 5, B_VFULL = 9, B_VEMPTY = 12, B_SREADY = 15, B_SFREE = 19,
-                B_PREADY = 23, B_OREADY = 25, B_PFREE = 27, B_TMEMPTR = 31;   // SREADY/SFREE/PFREE: [g*2 + buf]
+                B_PREADY = 23, B_PFREE = 27, B_TMEMPTR = 31;   // SREADY/SFREE/PREADY/PFREE: [g*2 + buf]
+  // PREADY is per P buffer like PFREE: a 4-arrival barrier shared by both buffers could be completed by one fast
+  // warp arriving for tiles j and j+1 before a slow warp has written its rows of P(j).  With one barrier per buffer a
+  // warp's next arrival on it (tile j+NP) is ordered behind PFREE, i.e. behind the P.V that consumed phase j.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // block -> (image, head, query super-tile)
   const int qtiles = (p.N + 128 * C::NQ - 1) / (128 * C::NQ);
@@ -112,10 +115,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       ptx::mbar_init(BAR(B_SREADY + i), 1);
       ptx::mbar_init(BAR(B_SFREE + i), 4);
       ptx::mbar_init(BAR(B_PFREE + i), 1);
-    }
-    for (int g = 0; g < 2; ++g) {
-      ptx::mbar_init(BAR(B_PREADY + g), 4);
-      ptx::mbar_init(BAR(B_OREADY + g), 1);
+      ptx::mbar_init(BAR(B_PREADY + i), 4);
     }
     ptx::fence_barrier_init();
   }
@@ -192,15 +192,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         const int st = j % C::NV;
         ptx::mbar_wait(BAR(B_VFULL + st), (uint32_t)((j / C::NV) & 1));
         for (int g = 0; g < nq_live; ++g) {
-          ptx::mbar_wait(BAR(B_PREADY + g), (uint32_t)(j & 1));
+          const int pb = j % C::NP;
+          ptx::mbar_wait(BAR(B_PREADY + g * 2 + pb), (uint32_t)((j / C::NP) & 1));
           ptx::tc_fence_after();
           const uint32_t vb = smem0 + C::OFF_V + st * C::VSTAGE;
 #pragma unroll
           for (int ks = 0; ks < C::BN / 16; ++ks)
-            ptx::umma_ts(tmem_base + C::col_o(g), tmem_base + C::col_p(g, j % C::NP) + ks * 8,
+            ptx::umma_ts(tmem_base + C::col_o(g), tmem_base + C::col_p(g, pb) + ks * 8,
                          ptx::make_sw128_desc(vb + ks * 16 * 128, C::KATOM, 1024), idesc, (j > 0) || (ks > 0));
-          ptx::umma_commit(BAR(B_OREADY + g));
-          ptx::umma_commit(BAR(B_PFREE + g * 2 + j % C::NP));
+          ptx::umma_commit(BAR(B_PFREE + g * 2 + pb));    // P buffer consumed == O_g holds tiles 0..j
         }
         ptx::umma_commit(BAR(B_VEMPTY + st));
       }
@@ -248,9 +248,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         // this tile's P buffer must have been consumed by its previous P.V ...
         const int pbuf = j % C::NP;
         ptx::mbar_wait(BAR(B_PFREE + g * 2 + pbuf), (uint32_t)(((j / C::NP) & 1) ^ 1));
-        // ... and O may only be rescaled once the P.V of the previous tile has landed (rare path)
+        // ... and O may only be rescaled once the P.V of the previous tile has landed (rare path): that is the PFREE
+        // phase of the previous tile's buffer, which this warp last waited on one phase earlier (no parity aliasing)
         if (j >= 1 && __any_sync(0xffffffffu, need)) {
-          ptx::mbar_wait(BAR(B_OREADY + g), (uint32_t)((j - 1) & 1));
+          ptx::mbar_wait(BAR(B_PFREE + g * 2 + (j - 1) % C::NP), (uint32_t)((((j - 1) / C::NP)) & 1));
           ptx::tc_fence_after();
           float o[C::DPV];
           tmem_ld_row<C::DPV>(tmem_base + lane_addr + C::col_o(g), o);
@@ -302,10 +303,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(BAR(B_PREADY + g));
+        if (lane == 0) ptx::mbar_arrive(BAR(B_PREADY + g * 2 + pbuf));
       }
       // epilogue: O / l -> fp16 -> global
-      ptx::mbar_wait(BAR(B_OREADY + g), (uint32_t)((n_kv - 1) & 1));
+      ptx::mbar_wait(BAR(B_PFREE + g * 2 + (n_kv - 1) % C::NP), (uint32_t)(((n_kv - 1) / C::NP) & 1));
       ptx::tc_fence_after();
       float o[C::DPV];
       tmem_ld_row<C::DPV>(tmem_base + lane_addr + C::col_o(g), o);
