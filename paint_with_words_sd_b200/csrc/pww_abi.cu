@@ -309,6 +309,14 @@ int pww_debug_set_timeline(void* device_buffer) {
   return PWW_OK;
 }
 
+// Test infrastructure (not declared in the public header): 1 = TMA-store epilogue where it applies (default),
+// 0 = per-thread global stores everywhere; for A/B timing of the tcgen05 forward kernel (see xattn_tc.cuh).
+int pww_debug_set_variant(int variant) {
+  if (variant < 0 || variant > 1) return PWW_ERR_BAD_ARG;
+  pww::tc::fwd_variant() = variant;
+  return PWW_OK;
+}
+
 int pww_attn_fwd_f16(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int D,
                      int64_t qkv_batch_stride, int64_t qkv_row_stride, int64_t o_batch_stride, int64_t o_row_stride,
                      float scale, void* stream) {

@@ -2,13 +2,16 @@
 //
 // Fused region of the reference's inj_forward (paint_with_words.py:87-118), per image b / head h / 128-row tile:
 //     S = Q_h K_h^T            UMMA M=128 N=80 K=D(+pad)   operands staged by TMA, accumulator in TMEM
-//     P = softmax(scale*(fp16(S) + g*M_b*w[b]))             one thread per query row, mask tile in shared memory
-//     O = P V_h                UMMA M=128 N=D K=80           P written to swizzled shared memory, V MN-major
-// Work unit = (image, row tile, head), flattened head-minor; every CTA owns a contiguous range of units so the
-// [128 x T] fp32 mask tile of a (image, tile) group is fetched once and reused by all heads of the group.
+//     P = softmax(scale*(S + g*M_b*w[b]))                   one thread per query row, mask tile in shared memory
+//     O = P V_h                UMMA M=128 N=D K=80           P (fp16) written over S in TMEM and read from there (TS form)
+// Work unit = (image, row tile, head).  Every CTA owns a contiguous range of units in an order (FwdWalk) that pairs one
+// image with a weight map and one without, alternates their heads, and fetches the [128 x T] fp32 mask tile of the
+// pair once for all heads.
 //
-// Warp roles (320 threads): warp 0 TMA producer | warp 1 UMMA issuer + TMEM owner | warps 2-5 softmax group 0 |
-// warps 6-9 softmax group 1.  Group g handles iterations it % 2 == g with its own S/O TMEM buffers and P buffer.
+// Forward-kernel warp roles (384 threads): warp 0 TMA producer for Q/K | warp 1 UMMA issuer S = Q K^T + TMEM owner |
+// warps 2-5 softmax group 0 | warps 6-9 softmax group 1 | warp 10 TMA producer for V and the mask | warp 11 UMMA issuer
+// O = P V.  Group g handles units it % 2 == g with its own score buffers (two per group for D <= 80) and O accumulator
+// in TMEM; the epilogue of a unit is deferred until the group has handed the next unit's P to the tensor pipe.
 //
 // Shared-memory tiles are 128-byte-swizzled "atoms" of 64 fp16 columns: Q [128 x 64], K/V [80 x 64] rows of 128 B.
 // TMA's out-of-bounds zero fill supplies every padding the UMMAs need (d >= D, token >= T, row >= N).
@@ -35,12 +38,18 @@ constexpr uint32_t kMaskBytes = kBM * kTP * 4;
 constexpr int kTmemCols = 512;
 constexpr int kMaxBatch = 256;   // images per launch (the C ABI splits larger batches)
 constexpr int kMaxLocal = 4;     // images one CTA's unit range can touch: B/148 + 2 <= 4 for B <= 256
-// TMEM column map (512 columns): S buffers 80 fp32 columns, P buffers 40 columns (80 packed fp16: the A operand of
-// the P.V UMMA is read straight from tensor memory), O buffers up to 160 columns.  For D = 160 there is no room for
-// separate P buffers: P aliases the first 40 columns of its S buffer.
-template <int D> __host__ __device__ constexpr uint32_t col_s(int g) { return g ? 96u : 0u; }
-template <int D> __host__ __device__ constexpr uint32_t col_p(int g) { return D == 160 ? (g ? 96u : 0u) : (g ? 232u : 192u); }
-template <int D> __host__ __device__ constexpr uint32_t col_o(int g) { return D == 160 ? (g ? 352u : 192u) : (g ? 384u : 288u); }
+// TMEM column map (512 columns).  Each softmax group g owns NSB score buffers of 80 fp32 columns and one O accumulator
+// of up to 160 columns.  P (80 packed fp16 = 40 columns, the A operand of the P.V UMMA, read straight from tensor
+// memory) overwrites the first 40 columns of the S buffer it was computed from, so a buffer cycles S -> P -> free and
+// the only thing that gates its reuse is the P.V that consumed it.  With NSB = 2 (D <= 80) the next S = Q K^T of a
+// group is issued while the group is still working on the current one: the softmax never waits for the tensor pipe.
+template <int D> __host__ __device__ constexpr int nsb() { return D <= 80 ? 2 : 1; }
+template <int D> __host__ __device__ constexpr uint32_t s_stride() { return D == 80 ? 80u : 96u; }
+template <int D> __host__ __device__ constexpr uint32_t o_stride() { return D <= 64 ? 64u : (D == 80 ? 96u : 160u); }
+template <int D> __host__ __device__ constexpr uint32_t col_s(int g, int buf) { return (uint32_t)(g * nsb<D>() + buf) * s_stride<D>(); }
+template <int D> __host__ __device__ constexpr uint32_t col_o(int g) { return 2u * nsb<D>() * s_stride<D>() + (uint32_t)g * o_stride<D>(); }
+static_assert(col_o<40>(1) + 48 <= 512 && col_o<64>(1) + 64 <= 512 && col_o<80>(1) + 96 <= 512 && col_o<160>(1) + 160 <= 512,
+              "TMEM budget");
 
 template <int D>
 struct Cfg {
@@ -60,9 +69,13 @@ struct Cfg {
   static constexpr int DPV = ONES ? (D + 16) / 16 * 16 : DP;   // UMMA N of P.V: 48, 64, 96, 160
   static constexpr uint32_t OFF_V = NQK * QKSTAGE;
   static constexpr uint32_t OFF_MASK = OFF_V + NV * VSTAGE;
-  static constexpr bool P_ALIAS = (D == 160);      // P overwrites S: the next S = Q K^T must wait for P.V, not for P
+  static constexpr int NSB = nsb<D>();             // score buffers per softmax group (see the TMEM map above)
   static constexpr uint32_t OFF_BAR = OFF_MASK + kMaskBytes;
   static constexpr uint32_t SMEM = OFF_BAR + 256 + 1024;   // + alignment slack
+  // TMA-store epilogue (forward-kernel variant bit 1): one [32 rows x D] fp16 staging tile per softmax warp
+  static constexpr uint32_t OFF_STG = OFF_BAR + 256;
+  static constexpr uint32_t STG_WARP = 32 * D * 2;
+  static constexpr uint32_t SMEM_EPI = OFF_STG + 8 * STG_WARP + 1024;
   // stats kernel: Q and K only
   static constexpr uint32_t SSTAGE = NA * (kQAtom + kKAtom);
   static constexpr int S_NSTAGE = (D <= 80) ? 3 : 2;
@@ -72,7 +85,7 @@ struct Cfg {
 
 // Debug timeline (test infrastructure): when TcParams::timeline is non-null, CTA 0 records clock64 per
 // (tag, iteration) in shared memory and dumps the table to global memory when the kernel ends.
-constexpr int kTlTags = 12, kTlIts = 40;
+constexpr int kTlTags = 14, kTlIts = 40;
 __shared__ long long tl_buf[kTlTags * kTlIts];
 #define PWW_TL(tag, it)                                                                      \
   do {                                                                                       \
@@ -112,24 +125,81 @@ struct UnitIter {
     }
   }
 };
-// Forward-kernel unit order: tile-major, image-minor, head-minor.  Consecutive (image, tile) groups alternate between
-// images, so every CTA's contiguous range mixes biased (mask + bias work) and unbiased units instead of some CTAs
-// getting only the expensive kind (the b-major order left ~10 % of the kernel as tail imbalance).
-struct UnitIterTM {
-  int b, tile, h, B, H;
-  __device__ __forceinline__ UnitIterTM(int u, int B_, int H_) : B(B_), H(H_) {
-    h = u % H_;
-    const int t = u / H_;
-    b = t % B_;
-    tile = t / B_;
-  }
-  __device__ __forceinline__ void next() {
-    if (++h == H) {
-      h = 0;
-      if (++b == B) { b = 0; ++tile; }
+// Forward-kernel unit order.  Units are tile-major; inside a row tile the images are visited in GROUPS that share one
+// [128 x T] mask tile in shared memory:
+//   * pair group: one biased image A (has a weight map) and one unbiased image U (classifier-free guidance puts as many
+//     of each in the batch).  2H units, head h = j/2, in the order  U A | A U | U A | ...  so that (1) biased and
+//     unbiased units alternate at the finest grain -- every CTA's contiguous range and both softmax groups get the same
+//     mix, whatever the image order in the batch -- (2) A's mask tile is reused by all H heads, and (3) the group ends
+//     with its mask no longer needed, so the next group's mask load overlaps the last units.
+//   * solo group: an image without a partner (all-biased or all-unbiased batches), H units head-minor.
+// s_img lists the biased images first (nb of them), then the unbiased ones.
+struct FwdUnit {
+  int b, h, tile;
+  int j, gsize;       // position inside the group, units in the group
+  int jl;             // last position whose unit reads the mask (gsize-1 when the group has no mask)
+  int mask_b;         // image whose mask tile the group uses, -1 = none
+};
+// Walks a CTA's contiguous unit range in that order; divisions only in the constructor.
+struct FwdWalk {
+  int B, H, nb, np, ng, jl_pair;
+  const int* img;
+  int tile, gi, j;    // row tile, group inside the tile (pair groups first, then solo groups), position in the group
+  __device__ __forceinline__ FwdWalk(int u, int B_, int H_, int nb_, const int* img_) : B(B_), H(H_), nb(nb_), img(img_) {
+    const int nu = B - nb;
+    np = nb < nu ? nb : nu;
+    ng = B - np;
+    const int jlast = 2 * H - 1;
+    jl_pair = ((((jlast ^ (jlast >> 1)) & 1) ^ 1) == 0) ? jlast : jlast - 1;
+    const int per_tile = B * H;
+    tile = u / per_tile;
+    int q = u - tile * per_tile;
+    if (q < np * 2 * H) {
+      gi = q / (2 * H);
+      j = q - gi * 2 * H;
+    } else {
+      q -= np * 2 * H;
+      const int solo = q / H;
+      gi = np + solo;
+      j = q - solo * H;
     }
   }
+  __device__ __forceinline__ void next() {
+    const int gsize = gi < np ? 2 * H : H;
+    if (++j == gsize) {
+      j = 0;
+      if (++gi == ng) { gi = 0; ++tile; }
+    }
+  }
+  __device__ __forceinline__ FwdUnit get() const {
+    FwdUnit r;
+    r.tile = tile;
+    r.j = j;
+    if (gi < np) {
+      r.gsize = 2 * H;
+      r.h = j >> 1;
+      const int unb = ((j ^ (j >> 1)) & 1) ^ 1;          // 1 = the unbiased image's unit
+      r.b = unb ? img[nb + gi] : img[gi];
+      r.mask_b = img[gi];
+      r.jl = jl_pair;
+    } else {
+      r.gsize = H;
+      r.h = j;
+      r.jl = H - 1;
+      if (2 * nb > B) { r.b = img[gi]; r.mask_b = r.b; }          // biased image without a partner
+      else { r.b = img[nb + gi]; r.mask_b = -1; }                 // unbiased image without a partner
+    }
+    return r;
+  }
 };
+// Position (inside its group) of the unit at which every softmax warp releases the group's mask tile: the last
+// mask-reading unit if the CTA's range [it - j_lo .., it + rest] contains it, else the last unit of the group in range.
+__device__ __forceinline__ int mask_release_pos(const FwdUnit& f, int it, int n_it) {
+  const int j_lo = f.j > it ? f.j - it : 0;
+  int j_hi = f.j + (n_it - 1 - it);
+  if (j_hi > f.gsize - 1) j_hi = f.gsize - 1;
+  return (f.jl >= j_lo && f.jl <= j_hi) ? f.jl : j_hi;
+}
 __device__ __forceinline__ void cta_range(int units, int& u0, int& u1) {
   u0 = (int)((long long)blockIdx.x * units / gridDim.x);
   u1 = (int)((long long)(blockIdx.x + 1) * units / gridDim.x);
@@ -143,10 +213,14 @@ __device__ __forceinline__ int image_widx(const XattnParams& p, int b) {
 // forward kernel
 // ---------------------------------------------------------------------------------------------------------
 // TT = 77 compiles the key-length checks away (the Stable Diffusion case); TT = 0 keeps them for any T <= 80.
-template <int D, int TT>
+// EPI_TMA: the epilogue goes through shared memory and TMA stores (one [32 x D] fp16 tile per softmax warp) instead of
+// 16-byte global stores from every thread (32 distinct lines per store instruction, 640 LSU wavefronts per unit);
+// both forms are built so one process can A/B them on the same device (pww_debug_set_variant).
+template <int D, int TT, bool EPI_TMA>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
-                    const __grid_constant__ CUtensorMap tmv, const TcParams tp) {
+                    const __grid_constant__ CUtensorMap tmv, const __grid_constant__ CUtensorMap tmo,
+                    const TcParams tp) {
   using C = Cfg<D>;
   const XattnParams& p = tp.x;
   extern __shared__ unsigned char smem_raw[];
@@ -155,8 +229,11 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   const uint32_t bar0 = smem0 + C::OFF_BAR;
   // barrier slots (8 bytes each)
   auto BAR = [&](int i) { return bar0 + 8u * i; };
+  // SREADY / PREADY / PVDONE are per score buffer, indexed [g*2 + buf]; a group's unit `local` uses buffer
+  // local % NSB in phase (local / NSB) & 1.  Every multi-arrival barrier keeps the rule that a warp's next arrival is
+  // causally behind the completion of the current phase (PREADY: via PVDONE -> next S; OFREE: via the next P.V).
   constexpr int B_QFULL = 0, B_QEMPTY = 4, B_VFULL = 8, B_VEMPTY = 11, B_MFULL = 14, B_MEMPTY = 15, B_SREADY = 16,
-                B_PREADY = 18, B_OREADY = 20, B_OFREE = 22, B_TMEMPTR = 24;
+                B_PREADY = 20, B_PVDONE = 24, B_OFREE = 28, B_TMEMPTR = 30;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int u0, u1;
   cta_range(tp.units, u0, u1);
@@ -164,7 +241,28 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   // per-image weight-map index and bias coefficient g(sigma)*M_b, staged once (no global loads in the loops)
   __shared__ int s_widx[kMaxBatch];
   __shared__ float s_coef[kMaxBatch];
+  __shared__ int s_img[kMaxBatch];             // biased images first, then unbiased (see fwd_unit)
+  __shared__ int s_nb;
   tl_init(tp);
+  if (warp == 2) {                             // stable partition of the images by "has a weight map"
+    int nb_total = 0;
+    for (int base = 0; base < p.B; base += 32) {
+      const int b = base + lane;
+      nb_total += __popc(__ballot_sync(0xffffffffu, b < p.B && image_widx(p, b) >= 0));
+    }
+    int cb = 0, cu = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int base = 0; base < p.B; base += 32) {
+      const int b = base + lane;
+      const bool valid = b < p.B, bi = valid && image_widx(p, b) >= 0;
+      const unsigned mb = __ballot_sync(0xffffffffu, bi), mu = __ballot_sync(0xffffffffu, valid && !bi);
+      if (bi) s_img[cb + __popc(mb & lt)] = b;
+      else if (valid) s_img[nb_total + cu + __popc(mu & lt)] = b;
+      cb += __popc(mb);
+      cu += __popc(mu);
+    }
+    if (lane == 0) s_nb = nb_total;
+  }
   for (int b = threadIdx.x; b < p.B; b += kFwdThreads) {
     const int wi = image_widx(p, b);
     s_widx[b] = wi;
@@ -175,6 +273,7 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     ptx::prefetch_tmap(&tmq);
     ptx::prefetch_tmap(&tmk);
     ptx::prefetch_tmap(&tmv);
+    if constexpr (EPI_TMA) ptx::prefetch_tmap(&tmo);
     for (int s = 0; s < C::NQK; ++s) {
       ptx::mbar_init(BAR(B_QFULL + s), 1);
       ptx::mbar_init(BAR(B_QEMPTY + s), 1);
@@ -185,12 +284,12 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     }
     ptx::mbar_init(BAR(B_MFULL), 1);
     ptx::mbar_init(BAR(B_MEMPTY), 8);          // one elected arrive per softmax warp
-    for (int g = 0; g < 2; ++g) {
-      ptx::mbar_init(BAR(B_SREADY + g), 1);
-      ptx::mbar_init(BAR(B_PREADY + g), 4);
-      ptx::mbar_init(BAR(B_OREADY + g), 1);
-      ptx::mbar_init(BAR(B_OFREE + g), 4);
+    for (int i = 0; i < 4; ++i) {
+      ptx::mbar_init(BAR(B_SREADY + i), 1);
+      ptx::mbar_init(BAR(B_PREADY + i), 4);
+      ptx::mbar_init(BAR(B_PVDONE + i), 1);
     }
+    for (int g = 0; g < 2; ++g) ptx::mbar_init(BAR(B_OFREE + g), 4);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<kTmemCols>(BAR(B_TMEMPTR));
@@ -202,8 +301,9 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   if (warp == 0) {
     // ===================================== TMA producer: Q and K tiles =====================================
     if (lane == 0) {
-      UnitIterTM uq(u0, p.B, p.H);
-      for (int it = 0; it < n_it; ++it, uq.next()) {
+      FwdWalk wq(u0, p.B, p.H, s_nb, s_img);
+      for (int it = 0; it < n_it; ++it, wq.next()) {
+        const FwdUnit uq = wq.get();
         const int st = it % C::NQK;
         ptx::mbar_wait(BAR(B_QEMPTY + st), (uint32_t)(((it / C::NQK) & 1) ^ 1));
         PWW_TL(1, it);
@@ -220,13 +320,15 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     __syncwarp();
   } else if (warp == 10) {
     // ===================================== TMA producer: mask tiles and V tiles =====================================
-    UnitIterTM uv(u0, p.B, p.H);
+    FwdWalk wv(u0, p.B, p.H, s_nb, s_img);
     int grp = -1;
-    for (int it = 0; it < n_it; ++it, uv.next()) {
-      if (it == 0 || uv.h == 0) {                 // first unit of an (image, tile) group: stage its mask tile
+    for (int it = 0; it < n_it; ++it, wv.next()) {
+      const FwdUnit uv = wv.get();
+      if (it == 0 || uv.j == 0) {                 // first unit of a group in this CTA's range: stage its mask tile
         ++grp;
         ptx::mbar_wait(BAR(B_MEMPTY), (uint32_t)((grp & 1) ^ 1));
-        const int widx = s_widx[uv.b];
+        // (a range that starts behind the group's last mask-reading unit does not need the tile)
+        const int widx = (uv.mask_b >= 0 && uv.j <= uv.jl) ? s_widx[uv.mask_b] : -1;
         if (widx >= 0) {
           const int rows = min(kBM, p.N - uv.tile * kBM);
           const uint32_t bytes = (uint32_t)rows * p.T * 4u;
@@ -257,15 +359,17 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       }
       __syncwarp();
     }
-  } else if (warp == 1) {
-    // ===================================== UMMA issuer: S = Q K^T =====================================
+  } else if (warp == 1 || warp == 11) {
+    // ===================================== UMMA issuers =====================================
     if (lane == 0) {
       constexpr uint32_t idesc_qk = ptx::make_idesc_f16(128, kTP, false, false);
-      for (int it = 0; it < n_it; ++it) {
-        const int st = it % C::NQK, g = it & 1, local = it >> 1;
+      constexpr uint32_t idesc_pv = ptx::make_idesc_f16(128, C::DPV, false, true);
+      // S[g][buf] = Q K^T of unit `it` (the group's unit `local`)
+      auto issue_qk = [&](int it) {
+        const int st = it % C::NQK, g = it & 1, local = it >> 1, buf = local % C::NSB, k = local / C::NSB;
         ptx::mbar_wait(BAR(B_QFULL + st), (uint32_t)((it / C::NQK) & 1));
-        if (local >= 1)                                  // S[g] consumed (and, when P aliases S, P.V done with it)
-          ptx::mbar_wait(BAR((C::P_ALIAS ? B_OREADY : B_PREADY) + g), (uint32_t)((local - 1) & 1));
+        if (k >= 1)                                      // the P.V that read P out of this buffer has finished
+          ptx::mbar_wait(BAR(B_PVDONE + g * 2 + buf), (uint32_t)((k - 1) & 1));
         PWW_TL(2, it);
         ptx::tc_fence_after();
         const uint32_t sb = smem0 + st * C::QKSTAGE;
@@ -273,22 +377,17 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         for (int ks = 0; ks < C::KSTEPS; ++ks) {
           const uint32_t qa = sb + (ks / 4) * kQAtom + (ks % 4) * 32;
           const uint32_t ka = sb + C::NA * kQAtom + (ks / 4) * kKAtom + (ks % 4) * 32;
-          ptx::umma_ss(tmem_base + col_s<D>(g), ptx::make_sw128_desc(qa, 16, 1024), ptx::make_sw128_desc(ka, 16, 1024),
-                       idesc_qk, ks > 0);
+          ptx::umma_ss(tmem_base + col_s<D>(g, buf), ptx::make_sw128_desc(qa, 16, 1024),
+                       ptx::make_sw128_desc(ka, 16, 1024), idesc_qk, ks > 0);
         }
-        ptx::umma_commit(BAR(B_SREADY + g));
+        ptx::umma_commit(BAR(B_SREADY + g * 2 + buf));
         ptx::umma_commit(BAR(B_QEMPTY + st));      // Q/K tiles are dead once S exists
         PWW_TL(4, it);
-      }
-    }
-    __syncwarp();
-  } else if (warp == 11) {
-    // ===================================== UMMA issuer: O = P V =====================================
-    if (lane == 0) {
-      constexpr uint32_t idesc_pv = ptx::make_idesc_f16(128, C::DPV, false, true);
-      for (int j = 0; j < n_it; ++j) {
-        const int st = j % C::NV, g = j & 1, local = j >> 1;
-        ptx::mbar_wait(BAR(B_PREADY + g), (uint32_t)(local & 1));
+      };
+      // O[g] = P V of unit `j`; P is read from the score buffer it overwrote
+      auto issue_pv = [&](int j) {
+        const int st = j % C::NV, g = j & 1, local = j >> 1, buf = local % C::NSB, k = local / C::NSB;
+        ptx::mbar_wait(BAR(B_PREADY + g * 2 + buf), (uint32_t)(k & 1));
         if (local >= 1) ptx::mbar_wait(BAR(B_OFREE + g), (uint32_t)((local - 1) & 1));
         ptx::mbar_wait(BAR(B_VFULL + st), (uint32_t)((j / C::NV) & 1));
         PWW_TL(3, j);
@@ -296,11 +395,18 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         const uint32_t vb = smem0 + C::OFF_V + st * C::VSTAGE;
 #pragma unroll
         for (int ks = 0; ks < kTP / 16; ++ks)          // A = P from tensor memory: 8 columns (16 fp16) per k-step
-          ptx::umma_ts(tmem_base + col_o<D>(g), tmem_base + col_p<D>(g) + ks * 8,
+          ptx::umma_ts(tmem_base + col_o<D>(g), tmem_base + col_s<D>(g, buf) + ks * 8,
                        ptx::make_sw128_desc(vb + ks * 16 * 128, kKAtom, 1024), idesc_pv, ks > 0);
-        ptx::umma_commit(BAR(B_OREADY + g));
+        ptx::umma_commit(BAR(B_PVDONE + g * 2 + buf));
         ptx::umma_commit(BAR(B_VEMPTY + st));
         PWW_TL(8, j);
+      };
+      // warp 1 issues every S = Q K^T, warp 11 every O = P V, both in unit order.  (One issuer warp per softmax group
+      // -- each issuing its group's S and P.V -- was tried and gave wrong results at D = 64: see profiles/.)
+      if (warp == 1) {
+        for (int it = 0; it < n_it; ++it) issue_qk(it);
+      } else {
+        for (int j = 0; j < n_it; ++j) issue_pv(j);
       }
     }
     __syncwarp();
@@ -311,18 +417,21 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     const uint32_t lane_addr = (uint32_t)((warp & 3) << 5) << 16;
     const float sl2 = p.scale * 1.4426950408889634f;
     const float* mask_row = reinterpret_cast<const float*>(smem_gen + C::OFF_MASK) + row * (TT ? TT : p.T);
-    UnitIterTM ui(u0, p.B, p.H);
+    FwdWalk ws(u0, p.B, p.H, s_nb, s_img);
     int grp = -1;
     // deferred epilogue state: iteration `pend` of this group has its P.V in flight / finished
-    int pend_local = -1, pend_n = 0;
+    int pend_local = -1, pend_n = 0, pend_b = 0, pend_h = 0;
     __half* pend_out = nullptr;
     float pend_inv = 0.f;
+    // TMA-store epilogue: this warp's [32 x D] fp16 staging tile (row = lane)
+    const uint32_t stg_off = C::OFF_STG + (uint32_t)(warp - 2) * C::STG_WARP;
 
     auto warp_arrive = [&](uint32_t bar) {       // one arrive per warp (barrier counts are per warp)
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar);
     };
     auto epilogue = [&]() {                      // O[g] (fp32, TMEM) -> * 1/rowsum -> fp16 -> global
+      ptx::mbar_wait(BAR(B_PVDONE + g * 2 + pend_local % C::NSB), (uint32_t)((pend_local / C::NSB) & 1));
       ptx::tc_fence_after();
       const uint32_t ta = tmem_base + lane_addr + col_o<D>(g);
       float o[C::DPV];
@@ -334,30 +443,54 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       ptx::tc_fence_before();
       warp_arrive(BAR(B_OFREE + g));             // O[g] is in registers: the next P.V may overwrite it
       const float inv = C::ONES ? 1.f / o[D] : pend_inv;
-      if (pend_n < p.N) {
+      if constexpr (EPI_TMA) {
+        // the staging tile is free once the previous store of this warp has been read out (lane 0 owns the groups)
+        if (lane == 0) ptx::bulk_wait_group_read0();
+        __syncwarp();
+        unsigned char* dst = smem_gen + stg_off + lane * (D * 2);
 #pragma unroll
         for (int c = 0; c < D / 8; ++c) {
           __align__(16) __half2 pk[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) pk[q] = __floats2half2_rn(o[c * 8 + 2 * q] * inv, o[c * 8 + 2 * q + 1] * inv);
-          reinterpret_cast<uint4*>(pend_out)[c] = *reinterpret_cast<const uint4*>(pk);
+          reinterpret_cast<uint4*>(dst)[c] = *reinterpret_cast<const uint4*>(pk);
+        }
+        ptx::fence_proxy_async_smem();           // generic-proxy writes -> visible to the TMA (async proxy)
+        __syncwarp();
+        const int n0 = pend_n - lane;            // first row of this warp's 32-row slice; rows >= N are clipped by TMA
+        if (lane == 0 && n0 < p.N) {
+          ptx::tma_store_4d(&tmo, smem0 + stg_off, 0, pend_h, n0, pend_b);
+          ptx::bulk_commit_group();
+        }
+      } else {
+        if (pend_n < p.N) {
+#pragma unroll
+          for (int c = 0; c < D / 8; ++c) {
+            __align__(16) __half2 pk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pk[q] = __floats2half2_rn(o[c * 8 + 2 * q] * inv, o[c * 8 + 2 * q + 1] * inv);
+            reinterpret_cast<uint4*>(pend_out)[c] = *reinterpret_cast<const uint4*>(pk);
+          }
         }
       }
     };
 
-    for (int it = 0; it < n_it; ++it, ui.next()) {
-      if (ui.h == 0 || it == 0) ++grp;
-      const bool last_of_group = (it == n_it - 1) || (ui.h == p.H - 1);
+    for (int it = 0; it < n_it; ++it, ws.next()) {
+      const FwdUnit ui = ws.get();
+      if (ui.j == 0 || it == 0) ++grp;
+      // every softmax warp releases the group's mask tile exactly once, at this position of the group
+      const bool release_here = (ui.j == mask_release_pos(ui, it, n_it));
       if ((it & 1) == g) {
-        const int local = it >> 1;
+        const int local = it >> 1, buf = local % C::NSB;
         const int widx = s_widx[ui.b];
         const float coef = s_coef[ui.b];
-        ptx::mbar_wait(BAR(B_SREADY + g), (uint32_t)(local & 1));
+        const uint32_t ts = tmem_base + lane_addr + col_s<D>(g, buf);
+        ptx::mbar_wait(BAR(B_SREADY + g * 2 + buf), (uint32_t)((local / C::NSB) & 1));
         if ((threadIdx.x & 127) == 64) PWW_TL(5, it);
         ptx::tc_fence_after();
         float s[kTP];
-        ptx::tmem_ld64_sync(tmem_base + lane_addr + col_s<D>(g), s);
-        ptx::tmem_ld16_sync(tmem_base + lane_addr + col_s<D>(g) + 64, s + 64);
+        ptx::tmem_ld64_sync(ts, s);
+        ptx::tmem_ld16_sync(ts + 64, s + 64);
         if ((threadIdx.x & 127) == 64) PWW_TL(0, it);
         // logits t_j = S_j + coef*w_j (unscaled), row max with 4 independent chains
         if (widx >= 0) {
@@ -372,6 +505,7 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
               if (j < p.T) s[j] = fmaf(coef, mask_row[j], s[j]);
           }
         }
+        if (release_here) warp_arrive(BAR(B_MEMPTY));   // the mask values are in registers: the next tile may land
         if constexpr (TT == 77) {
           s[77] = s[78] = s[79] = -INFINITY;
         } else {
@@ -412,30 +546,33 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
                 __float2half(1.0f);
           }
         }
-        // the previous iteration's P.V must be done before its P buffer is overwritten
         if (lane == 0) { const int qd = warp & 3; PWW_TL((qd == 2 ? 7 : (qd == 3 ? 9 : (qd == 0 ? 10 : 11))), it); }
-        if (pend_local >= 0) ptx::mbar_wait(BAR(B_OREADY + g), (uint32_t)(pend_local & 1));
-        ptx::tmem_st32_u32(tmem_base + lane_addr + col_p<D>(g), pk);          // P row -> tensor memory (packed fp16)
-        ptx::tmem_st8_u32(tmem_base + lane_addr + col_p<D>(g) + 32, pk + 32);
+        // P row (packed fp16) over the S row it came from: this thread has the whole row in registers
+        ptx::tmem_st32_u32(ts, pk);
+        ptx::tmem_st8_u32(ts + 32, pk + 32);
         ptx::tmem_st_wait();
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
-        warp_arrive(BAR(B_PREADY + g));
+        warp_arrive(BAR(B_PREADY + g * 2 + buf));
         if ((threadIdx.x & 127) == 64) PWW_TL(6, it);
-        if (last_of_group) warp_arrive(BAR(B_MEMPTY));
-        if (pend_local >= 0) epilogue();           // overlaps with this iteration's P.V
+        if (pend_local >= 0) {                     // overlaps with this iteration's P.V
+          epilogue();
+          if ((threadIdx.x & 127) == 64) PWW_TL(12, it);
+        }
 
         pend_local = local;
         pend_n = ui.tile * kBM + row;
+        pend_b = ui.b;
+        pend_h = ui.h;
         pend_out = p.out + (int64_t)ui.b * p.o_bs + (int64_t)pend_n * p.o_rs + ui.h * D;
         pend_inv = 1.f / sum;
-      } else if (last_of_group) {
-        warp_arrive(BAR(B_MEMPTY));
+      } else if (release_here) {
+        warp_arrive(BAR(B_MEMPTY));                     // the other group's unit: this warp's mask reads are all behind it
       }
     }
-    if (pend_local >= 0) {
-      ptx::mbar_wait(BAR(B_OREADY + g), (uint32_t)(pend_local & 1));
-      epilogue();
+    if (pend_local >= 0) epilogue();
+    if constexpr (EPI_TMA) {
+      if (lane == 0) ptx::bulk_wait_group0();    // the staging tile must outlive the last store
     }
   }
   ptx::tc_fence_before();
@@ -752,6 +889,49 @@ inline long long*& debug_timeline() {
   static long long* ptr = nullptr;
   return ptr;
 }
+// Forward-kernel epilogue: 1 = TMA stores where they apply (see EPI_TMA on xattn_fwd_tc_kernel), 0 = per-thread global
+// stores everywhere; pww_debug_set_variant overrides it for A/B timing.
+constexpr int kDefaultFwdVariant = 1;
+inline int& fwd_variant() {
+  static int v = kDefaultFwdVariant;
+  return v;
+}
+// Row-major [B, L, H, D] fp16 output as a TMA tensor: boxes of [D x 1 x rows x 1], no swizzle.
+inline bool make_tmap_out(CUtensorMap* m, const void* base, int D, int H, int L, int B, int64_t row_stride,
+                          int64_t batch_stride, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)H, (cuuint64_t)L, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)D * 2, (cuuint64_t)row_stride * 2, (cuuint64_t)batch_stride * 2};
+  cuuint32_t box[4] = {(cuuint32_t)D, 1, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int D, bool EPI_TMA>
+cudaError_t launch_fwd_var(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
+                           const TcParams& tp, cudaStream_t s) {
+  using C = Cfg<D>;
+  constexpr uint32_t smem = EPI_TMA ? C::SMEM_EPI : C::SMEM;
+  static_assert(smem <= 232448 - 8192, "shared memory budget (dynamic + static tables)");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(xattn_fwd_tc_kernel<D, 77, EPI_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(xattn_fwd_tc_kernel<D, 0, EPI_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int grid = tp.units < num_sms() ? tp.units : num_sms();
+  if (tp.x.T == 77)
+    xattn_fwd_tc_kernel<D, 77, EPI_TMA><<<grid, kFwdThreads, smem, s>>>(tq, tk, tv, to, tp);
+  else
+    xattn_fwd_tc_kernel<D, 0, EPI_TMA><<<grid, kFwdThreads, smem, s>>>(tq, tk, tv, to, tp);
+  return cudaGetLastError();
+}
 
 template <int D>
 cudaError_t launch_fwd(const XattnParams& x, cudaStream_t s) {
@@ -768,20 +948,16 @@ cudaError_t launch_fwd(const XattnParams& x, cudaStream_t s) {
   tp.units = x.B * tp.tiles * x.H;
   tp.k_batched = x.k_bs > 0 ? 1 : 0;
   tp.timeline = debug_timeline();
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(xattn_fwd_tc_kernel<D, 77>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(xattn_fwd_tc_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
+  // the TMA-store epilogue needs a 16-byte aligned, 16-byte strided output; shared memory has room for its staging
+  // tiles only at D = 40 (the 64x64-latent layers, where this kernel spends its time)
+  CUtensorMap to = tq;
+  if constexpr (D == 40) {
+    const bool tma_ok = (reinterpret_cast<uintptr_t>(x.out) & 15u) == 0 && (x.o_rs * 2) % 16 == 0 &&
+                        (x.o_bs * 2) % 16 == 0 && x.o_bs > 0;
+    if (fwd_variant() == 1 && tma_ok && make_tmap_out(&to, x.out, D, x.H, x.N, x.B, x.o_rs, x.o_bs, 32))
+      return launch_fwd_var<D, true>(tq, tk, tv, to, tp, s);
   }
-  const int grid = tp.units < num_sms() ? tp.units : num_sms();
-  if (x.T == 77)
-    xattn_fwd_tc_kernel<D, 77><<<grid, kFwdThreads, C::SMEM, s>>>(tq, tk, tv, tp);
-  else
-    xattn_fwd_tc_kernel<D, 0><<<grid, kFwdThreads, C::SMEM, s>>>(tq, tk, tv, tp);
-  return cudaGetLastError();
+  return launch_fwd_var<D, false>(tq, tk, tv, to, tp, s);
 }
 
 template <int D>

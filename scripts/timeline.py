@@ -25,7 +25,7 @@ L.pww_debug_set_timeline.argtypes = [ctypes.c_void_p]
 for _ in range(3):
     A.cross_attention(q, k, v, H, D ** -0.5, w, idx, _native.PWW_STAT_MAX, gs)
 torch.cuda.synchronize()
-TAGS, ITS = 12, 40
+TAGS, ITS = 14, 40
 which = sys.argv[1] if len(sys.argv) > 1 else "stats"
 buf = torch.zeros(TAGS * ITS, dtype=torch.int64, device=dev)
 st = A._state(torch.device("cuda", 0))
@@ -45,8 +45,8 @@ torch.cuda.synchronize()
 L.pww_debug_set_timeline(None)
 tab = buf.cpu().view(TAGS, ITS)
 t0 = int(tab[tab > 0].min())
-names = {0: "wg_tmem_loaded", 11: "wg_mask_ready", 1: "prod_load", 2: "mma_full", 3: "mma_sfree/pready", 4: "mma_issued", 5: "wg_sready", 6: "wg_sfree/pready_arr",
-         7: "wg_done", 8: "mma_pv_issued", 9: "wg_oready", 10: "wg_epi_done", }
+names = {0: "wg_tmem_loaded", 1: "prod_load", 2: "qk_waits_done", 3: "pv_waits_done", 4: "qk_issued", 5: "wg_sready", 6: "wg_pready_arr",
+         7: "wg_math_done_q2", 8: "pv_issued", 9: "wg_math_done_q3", 10: "wg_math_done_q0", 11: "wg_math_done_q1", 12: "wg_epi_done"}
 rows = []
 for tag in range(TAGS):
     for it in range(ITS):
@@ -54,8 +54,9 @@ for tag in range(TAGS):
             rows.append((int(tab[tag, it]) - t0, tag, it))
 for t, tag, it in sorted(rows)[:150]:
     print(f"{t:8d}  {names.get(tag, tag):20s} it={it}")
-print("---- per-iteration stamps (cycles since start): it, prod_load, mma_qk_issued, wg_sready, wg_math_done, wg_p_arrived, mma_pv_issued, wg_epi_done")
+print("---- per-iteration stamps (cycles since start)")
+print("it  prod_load qk_wait qk_issued | sready tmem_ld math_done(q2,q3,q0,q1) pready_arr epi_done | pv_wait pv_issued")
 for it in range(ITS):
     if tab[1, it] > 0:
         f = lambda tag: (int(tab[tag, it]) - t0) if tab[tag, it] > 0 else -1
-        print(it, f(1), f(4), f(5), "math done per warp(q2,q3,q0,q1):", f(7), f(9), f(10), f(11), "p_arr", f(6), "pv", f(8))
+        print(f"{it:2d} {f(1):7d} {f(2):7d} {f(4):7d} | {f(5):7d} {f(0):7d}  {f(7):7d} {f(9):7d} {f(10):7d} {f(11):7d}  {f(6):7d} {f(12):7d} | {f(3):7d} {f(8):7d}")
