@@ -253,6 +253,49 @@ def xattn_roofline(device, B: int, biased: int, N=4096, H=8, D=40, T=77, target_
     return {"us_stats": t_stats, "us_fwd": t_fwd, "alg_bytes": alg_bytes, "sets": nsets, "iters": iters}
 
 
+def eager_torch_xattn_us(device, N=4096, H=8, D=40, T=77, iters=20, dtype=torch.float16):
+    """Comparison only ("time the reference path on the B200"): the op sequence of the reference's
+    inj_forward between to_q/to_k/to_v and to_out (paint_with_words.py:83-118) as eager PyTorch on this device, for
+    one conditional call (bias = 0.4*w*log(1+sigma)*qk.max()) plus one unconditional call -- the work one B=2 launch
+    pair (pww_xattn_stats_f16 + pww_xattn_fwd_f16) of this repo does.  Returns microseconds per cond+uncond pair."""
+    C = H * D
+    g = torch.Generator(device="cpu").manual_seed(0)
+    q = (torch.randn(1, N, C, generator=g) * 0.5).to(device=device, dtype=dtype)
+    k = (torch.randn(1, T, C, generator=g) * 0.5).to(device=device, dtype=dtype)
+    v = (torch.randn(1, T, C, generator=g) * 0.5).to(device=device, dtype=dtype)
+    w = (torch.rand(N, T, generator=g) > 0.8).float().to(device)
+    sigma = torch.tensor(7.0)
+    scale = D ** -0.5
+
+    def heads_to_batch(x):
+        b, n, _ = x.shape
+        return x.reshape(b, n, H, D).permute(0, 2, 1, 3).reshape(b * H, n, D)
+
+    def call(biased):
+        qh, kh, vh = heads_to_batch(q), heads_to_batch(k), heads_to_batch(v)
+        s = torch.matmul(qh, kh.transpose(-1, -2))
+        bias = 0.4 * w * math.log(1 + float(sigma)) * s.max() if biased else 0.0
+        p = ((s + bias) * scale).softmax(dim=-1).to(dtype)
+        o = torch.matmul(p, vh)
+        return o.reshape(1, H, N, D).permute(0, 2, 1, 3).reshape(1, N, C)
+
+    for _ in range(3):
+        call(True); call(False)
+    if device.type != "cuda":
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            call(True); call(False)
+        return (time.perf_counter() - t0) * 1e6 / iters
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(device)
+    e0.record()
+    for _ in range(iters):
+        call(True); call(False)
+    e1.record()
+    torch.cuda.synchronize(device)
+    return e0.elapsed_time(e1) * 1e3 / iters
+
+
 # ------------------------------------------------------------------------------------------------
 # main arm
 # ------------------------------------------------------------------------------------------------
@@ -426,6 +469,14 @@ def main():
         except Exception as e:  # keep the headline even if the micro-bench fails
             line["roofline"] = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
                                 "traffic": None, "error": repr(e)}
+        try:    # comparison only: the reference's eager op sequence on this GPU, same shapes, cond + uncond call
+            us = eager_torch_xattn_us(device)
+            line["roofline"]["eager_torch_fp16"] = {
+                "us_per_cond_uncond_pair": us,
+                "note": "reference inj_forward op sequence (heads->batch copies, QK^T, max, bias add, softmax, PV) as eager "
+                        "PyTorch fp16 on this GPU at N=4096 C=320; compare with stats_kernel_us + us_per_launch"}
+        except Exception as e:
+            line["roofline"]["eager_torch_fp16"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 r = cpu_reference(max_timed_steps=2, warmup=0, budget_s=45.0)
