@@ -317,6 +317,14 @@ int pww_debug_set_variant(int variant) {
   return PWW_OK;
 }
 
+// Test infrastructure (not declared in the public header): replay the forward kernel's unit schedule on the host.
+// wmap_index and out are HOST pointers; out receives 8 int32 per unit (see fwd_schedule_host); returns the number of
+// units written or a negative value for bad arguments.  No GPU needed.
+int pww_debug_fwd_schedule(int B, int H, int tiles, int grid, const int* wmap_index, int* out) {
+  if (!wmap_index || !out) return PWW_ERR_BAD_ARG;
+  return pww::tc::fwd_schedule_host(B, H, tiles, grid, wmap_index, out);
+}
+
 int pww_attn_fwd_f16(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int D,
                      int64_t qkv_batch_stride, int64_t qkv_row_stride, int64_t o_batch_stride, int64_t o_row_stride,
                      float scale, void* stream) {

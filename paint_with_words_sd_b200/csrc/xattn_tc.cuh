@@ -145,7 +145,7 @@ struct FwdWalk {
   int B, H, nb, np, ng, jl_pair;
   const int* img;
   int tile, gi, j;    // row tile, group inside the tile (pair groups first, then solo groups), position in the group
-  __device__ __forceinline__ FwdWalk(int u, int B_, int H_, int nb_, const int* img_) : B(B_), H(H_), nb(nb_), img(img_) {
+  __host__ __device__ __forceinline__ FwdWalk(int u, int B_, int H_, int nb_, const int* img_) : B(B_), H(H_), nb(nb_), img(img_) {
     const int nu = B - nb;
     np = nb < nu ? nb : nu;
     ng = B - np;
@@ -164,14 +164,14 @@ struct FwdWalk {
       j = q - solo * H;
     }
   }
-  __device__ __forceinline__ void next() {
+  __host__ __device__ __forceinline__ void next() {
     const int gsize = gi < np ? 2 * H : H;
     if (++j == gsize) {
       j = 0;
       if (++gi == ng) { gi = 0; ++tile; }
     }
   }
-  __device__ __forceinline__ FwdUnit get() const {
+  __host__ __device__ __forceinline__ FwdUnit get() const {
     FwdUnit r;
     r.tile = tile;
     r.j = j;
@@ -194,7 +194,7 @@ struct FwdWalk {
 };
 // Position (inside its group) of the unit at which every softmax warp releases the group's mask tile: the last
 // mask-reading unit if the CTA's range [it - j_lo .., it + rest] contains it, else the last unit of the group in range.
-__device__ __forceinline__ int mask_release_pos(const FwdUnit& f, int it, int n_it) {
+__host__ __device__ __forceinline__ int mask_release_pos(const FwdUnit& f, int it, int n_it) {
   const int j_lo = f.j > it ? f.j - it : 0;
   int j_hi = f.j + (n_it - 1 - it);
   if (j_hi > f.gsize - 1) j_hi = f.gsize - 1;
@@ -889,6 +889,35 @@ inline long long*& debug_timeline() {
   static long long* ptr = nullptr;
   return ptr;
 }
+// Host replay of the forward kernel's unit schedule (test infrastructure): the same FwdWalk / cta_range /
+// mask_release_pos code the kernel runs, executed on the CPU.  out[u] = {cta, it, b, h, tile, group_id, mask_b,
+// releases_mask_here} for every unit in launch order of each CTA.
+inline int fwd_schedule_host(int B, int H, int tiles, int grid, const int* wmap_index, int* out) {
+  if (B <= 0 || B > kMaxBatch || H <= 0 || tiles <= 0 || grid <= 0) return -1;
+  int img[kMaxBatch];
+  int nb = 0;
+  for (int b = 0; b < B; ++b) if (wmap_index[b] >= 0) img[nb++] = b;
+  int nu = 0;
+  for (int b = 0; b < B; ++b) if (wmap_index[b] < 0) img[nb + nu++] = b;
+  const long long units = (long long)B * H * tiles;
+  int row = 0;
+  for (int cta = 0; cta < grid; ++cta) {
+    const int u0 = (int)((long long)cta * units / grid), u1 = (int)((long long)(cta + 1) * units / grid);
+    const int n_it = u1 - u0;
+    if (n_it == 0) continue;
+    FwdWalk w(u0, B, H, nb, img);
+    int grp = -1;
+    for (int it = 0; it < n_it; ++it, w.next()) {
+      const FwdUnit f = w.get();
+      if (f.j == 0 || it == 0) ++grp;
+      int* o = out + 8 * (row++);
+      o[0] = cta; o[1] = it; o[2] = f.b; o[3] = f.h; o[4] = f.tile; o[5] = grp; o[6] = f.mask_b;
+      o[7] = (f.j == mask_release_pos(f, it, n_it)) ? 1 : 0;
+    }
+  }
+  return row;
+}
+
 // Forward-kernel epilogue: 1 = TMA stores where they apply (see EPI_TMA on xattn_fwd_tc_kernel), 0 = per-thread global
 // stores everywhere; pww_debug_set_variant overrides it for A/B timing.
 constexpr int kDefaultFwdVariant = 1;
