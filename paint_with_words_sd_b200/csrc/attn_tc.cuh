@@ -2,15 +2,19 @@
 // attention forward on tcgen05 tensor cores: softmax(scale * Q_h K_h^T) V_h with keys = the image's own N pixels.
 //
 // One CTA = (image, head, NQ query tiles of 128 rows).  K and V tiles of BN keys stream through two TMA rings and are
-// shared by the NQ query tiles; softmax group g (4 warps, one thread per query row) owns tile g's S and O accumulators
-// in TMEM and its P buffer in shared memory:
-//     S_g = Q_g K_j^T   (UMMA M=128 N=BN)      -> TMEM
+// shared by the NQ query tiles; softmax group g (4 warps, one thread per query row) owns tile g's S, P and O buffers
+// in tensor memory:
+//     S_g = Q_g K_j^T   (UMMA M=128 N=BN)      -> TMEM, double-buffered: S_g(j+1) is issued while softmax(j) runs
 //     online softmax with LAZY rescaling: the running max only moves (and O_g is rescaled in TMEM) when the tile max
 //       exceeds it by more than 2^8, so the correction pass is rare; P = 2^(s - m) <= 256 fits fp16
-//     O_g += P V_j      (UMMA M=128 N=D K=BN, V MN-major) accumulating in TMEM over all key tiles
-// Warp roles (384 threads = 3 warpgroups): warpgroup 0 = {0 Q+K producer, 1 S-UMMA issuer + TMEM owner, 2 V producer,
-// 3 PV-UMMA issuer} gives its registers away (setmaxnreg); warpgroups 1 and 2 are the two softmax groups.  Padding (d >= D, key >= N, row >= N) comes from TMA out-of-bounds zero fill; padded keys of
-// the last tile are masked to -inf.
+//     P_g (packed fp16)                         -> TMEM (double-buffered where it fits), the A operand of
+//     O_g += P_g V_j    (TS-form UMMA M=128 N=D K=BN, V MN-major) accumulating in TMEM over all key tiles;
+//       for D = 40 / 80 a ones column in V makes accumulator column D the row sum of the fp16 P that was multiplied
+// Warp roles (384 threads): warp 0 Q+K TMA producer | warp 1 S-UMMA issuer + TMEM owner | warp 2 V TMA producer |
+// warp 3 PV-UMMA issuer | warps 4-7 and 8-11 the two softmax groups.  Every barrier that takes several arrivals per
+// phase is per buffer, so a warp's next arrival on it is causally behind the completion of the current phase.
+// Padding (d >= D, key >= N, row >= N) comes from TMA out-of-bounds zero fill; padded keys of the last tile are masked
+// to -inf.
 #pragma once
 #include "ptx_sm100.cuh"
 #include "pww_common.cuh"
@@ -124,8 +128,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + C::OFF_BAR + 8 * B_TMEMPTR);
-  // register re-distribution: the data-movement warpgroup keeps 40 registers, the softmax warpgroups grow to 232
-  // (setmaxnreg re-distribution is not needed: the two-pass softmax keeps every role under the 168-register budget)
+  // (no setmaxnreg re-distribution: the two-pass softmax keeps every role under the 168-register budget)
 
   if (warp == 0) {
     // ------------------------------------------------ producer: Q tiles once, then the K ring

@@ -5,6 +5,7 @@
 #include "pww_common.cuh"
 #include "xattn_simt.cuh"
 #include "xattn_tc.cuh"
+#include "xattn_tc_g4.cuh"
 #include "attn_tc.cuh"
 #include "unet_ops.cuh"
 #include <stdlib.h>
@@ -310,9 +311,10 @@ int pww_debug_set_timeline(void* device_buffer) {
 }
 
 // Test infrastructure (not declared in the public header): 1 = TMA-store epilogue where it applies (default),
-// 0 = per-thread global stores everywhere; for A/B timing of the tcgen05 forward kernel (see xattn_tc.cuh).
+// 0 = per-thread global stores everywhere, 2 = the experimental four-group kernel at D = 40 (xattn_tc_g4.cuh);
+// for A/B timing of the tcgen05 forward kernels.
 int pww_debug_set_variant(int variant) {
-  if (variant < 0 || variant > 1) return PWW_ERR_BAD_ARG;
+  if (variant < 0 || variant > 2) return PWW_ERR_BAD_ARG;
   pww::tc::fwd_variant() = variant;
   return PWW_OK;
 }

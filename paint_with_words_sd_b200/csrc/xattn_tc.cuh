@@ -940,6 +940,9 @@ inline bool make_tmap_out(CUtensorMap* m, const void* base, int D, int H, int L,
   return r == CUDA_SUCCESS;
 }
 
+cudaError_t launch_fwd_g4(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
+                          const TcParams& tp, cudaStream_t s);   // xattn_tc_g4.cuh
+
 template <int D, bool EPI_TMA>
 cudaError_t launch_fwd_var(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
                            const TcParams& tp, cudaStream_t s) {
@@ -983,8 +986,10 @@ cudaError_t launch_fwd(const XattnParams& x, cudaStream_t s) {
   if constexpr (D == 40) {
     const bool tma_ok = (reinterpret_cast<uintptr_t>(x.out) & 15u) == 0 && (x.o_rs * 2) % 16 == 0 &&
                         (x.o_bs * 2) % 16 == 0 && x.o_bs > 0;
-    if (fwd_variant() == 1 && tma_ok && make_tmap_out(&to, x.out, D, x.H, x.N, x.B, x.o_rs, x.o_bs, 32))
+    if (fwd_variant() >= 1 && tma_ok && make_tmap_out(&to, x.out, D, x.H, x.N, x.B, x.o_rs, x.o_bs, 32)) {
+      if (fwd_variant() == 2) return launch_fwd_g4(tq, tk, tv, to, tp, s);   // experimental, see xattn_tc_g4.cuh
       return launch_fwd_var<D, true>(tq, tk, tv, to, tp, s);
+    }
   }
   return launch_fwd_var<D, false>(tq, tk, tv, to, tp, s);
 }
