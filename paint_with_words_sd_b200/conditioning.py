@@ -88,6 +88,33 @@ def _tokens_img_attention_weight(img_context_seperated, tokenized_texts, ratio: 
     return out.reshape(r0, r1, len(token_lis)) if original_shape else out
 
 
+def _tokens_img_attention_factors(img_context_seperated, tokenized_texts, ratio: int = 8):
+    """The same weight map as `_tokens_img_attention_weight`, kept in the factored form it is built from:
+    W[n, t] = sum_r M[n, r] * C[t, r] with M [N, R] fp32 (column r = region r's resized strength mask,
+    paint_with_words.py:269-272) and C [T, R] fp32 (how many matched label spans of region r cover token t,
+    paint_with_words.py:259-268; 0/1 unless labels repeat or overlap).  Regions whose label is not in the prompt are
+    dropped exactly like the reference drops them.  R is the number of painted regions (5 in the reference's examples),
+    so (M, C) is N*R + 77*R numbers instead of N*77 -- the packed mask format of SURVEY 8f-4: the bias
+    g*M_b*W = (g*M_b*M) C^T is one extra k-step of the Q K^T UMMA instead of 77 loads and FMAs per query row.
+    Not consumed by a kernel yet."""
+    token_lis = tokenized_texts["input_ids"][0].tolist()
+    dim0, dim1 = img_context_seperated[0][1].shape
+    r0, r1 = always_round(dim0 / ratio), always_round(dim1 / ratio)
+    cols, counts = [], []
+    for label, mask in img_context_seperated:
+        starts = _match_positions(token_lis, label)
+        if not starts:
+            continue
+        cnt = torch.zeros(len(token_lis), dtype=torch.float32)
+        for s in starts:
+            cnt[s:s + len(label)] += 1.0
+        cols.append(_img_importance_flatten(mask, r0, r1).reshape(-1))
+        counts.append(cnt)
+    if not cols:
+        return torch.zeros((r0 * r1, 0), dtype=torch.float32), torch.zeros((len(token_lis), 0), dtype=torch.float32)
+    return torch.stack(cols, dim=1), torch.stack(counts, dim=1)
+
+
 def _extract_seed_and_sigma_from_context(color_context: dict, ignore_seed: int = -1):
     """paint_with_words.py:279-297: "label,strength[,seed[,blur_sigma]]".  Mutates `color_context`."""
     extra_seeds: Dict[int, int] = {}

@@ -76,6 +76,40 @@ def test_repeated_and_missing_labels_accumulate():
     assert len(cat_cols) == 2 and float(w[0, cat_cols[0]]) == 3.0      # "cat" + "a cat" both hit the column
 
 
+@pytest.mark.parametrize("name,size", [("aurora", 512), ("cat_dog", 256)])
+def test_factored_weight_map_reproduces_the_dense_one(name, size):
+    """W = M C^T (SURVEY 8f-4 packed mask format): bit-exact where every token belongs to one region (the reference's
+    own examples), and the factors are tiny compared with the dense map."""
+    tok = SimpleWordTokenizer()
+    s = SETTINGS[name]
+    ctx, _, _ = C._extract_seed_and_sigma_from_context(dict(s["ctx"]))
+    sep, _, _ = C._image_context_seperator(color_map_image(name, size), ctx, tok)
+    ids = tok([s["prompt"]], padding="max_length", max_length=77, truncation=True, return_tensors="pt")
+    for ratio in (8, 16, 32, 64):
+        w = C._tokens_img_attention_weight(sep, ids, ratio=ratio)
+        m, c = C._tokens_img_attention_factors(sep, ids, ratio=ratio)
+        assert m.shape[0] == w.shape[0] and c.shape[0] == 77 and m.shape[1] == c.shape[1] <= len(sep)
+        assert torch.equal(m @ c.T, w)
+        if w.shape[0] >= 1024:
+            assert m.numel() + c.numel() < w.numel() / 5
+        # fp16 storage of the factors (what a UMMA operand would hold) stays far inside the attention tolerance
+        w16 = m.half().float() @ c.T
+        assert (w16 - w).abs().max().item() <= 2 ** -11 * w.abs().max().item()
+
+
+def test_factored_weight_map_with_repeats_and_missing_labels():
+    tok = SimpleWordTokenizer()
+    ids = tok(["a cat and a cat on a mat"], padding="max_length", max_length=77, truncation=True, return_tensors="pt")
+    m1 = torch.zeros(64, 64); m1[:32] = 1.5
+    m2 = torch.zeros(64, 64); m2[16:48, 8:40] = 0.7
+    sep = [(tok("cat")["input_ids"][1:-1], m1), (tok("a cat")["input_ids"][1:-1], m2), (tok("dog")["input_ids"][1:-1], m1)]
+    w = C._tokens_img_attention_weight(sep, ids, ratio=8)
+    m, c = C._tokens_img_attention_factors(sep, ids, ratio=8)
+    assert m.shape[1] == 2                                   # "dog" is not in the prompt: dropped like the reference does
+    assert float(c.max()) == 2.0 or float(c.sum()) == 6.0    # "cat" twice (1 token), "a cat" twice (2 tokens)
+    assert torch.allclose(m @ c.T, w, rtol=0, atol=1e-6)
+
+
 def test_orig_fallback_matches_oracle(golden):
     w_orig = torch.from_numpy(golden["attention"]["w_orig"])
     assert torch.equal(C.expand_orig_weight_map(w_orig, 64), O.orig_map_fallback(w_orig, 64))
