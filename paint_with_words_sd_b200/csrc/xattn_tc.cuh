@@ -72,9 +72,15 @@ struct Cfg {
   static constexpr int NSB = nsb<D>();             // score buffers per softmax group (see the TMEM map above)
   static constexpr uint32_t OFF_BAR = OFF_MASK + kMaskBytes;
   static constexpr uint32_t SMEM = OFF_BAR + 256 + 1024;   // + alignment slack
-  // TMA-store epilogue (forward-kernel variant bit 1): one [32 rows x D] fp16 staging tile per softmax warp
-  static constexpr uint32_t OFF_STG = OFF_BAR + 256;
-  static constexpr uint32_t STG_WARP = 32 * D * 2;
+  // TMA-store epilogue: one [32 rows x EPI_CW columns] fp16 staging tile per softmax warp, stored in D / EPI_CW passes.
+  // D = 40: the whole row in one pass, plain layout (80-byte rows are bank-conflict free).  D = 64: one pass, rows of
+  // 128 bytes in the 128-byte swizzle (plain rows would make every 16-byte store an 8-way bank conflict).  D = 80, 160:
+  // 40-column passes so the staging fits beside the operand rings.
+  static constexpr int EPI_CW = (D == 64) ? 64 : 40;
+  static constexpr int EPI_NPASS = D / EPI_CW;
+  static constexpr bool EPI_SW = (D == 64);
+  static constexpr uint32_t OFF_STG = OFF_BAR + (EPI_SW ? 1024 : 256);
+  static constexpr uint32_t STG_WARP = 32 * EPI_CW * 2;
   static constexpr uint32_t SMEM_EPI = OFF_STG + 8 * STG_WARP + 1024;
   // stats kernel: Q and K only
   static constexpr uint32_t SSTAGE = NA * (kQAtom + kKAtom);
@@ -444,23 +450,28 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       warp_arrive(BAR(B_OFREE + g));             // O[g] is in registers: the next P.V may overwrite it
       const float inv = C::ONES ? 1.f / o[D] : pend_inv;
       if constexpr (EPI_TMA) {
-        // the staging tile is free once the previous store of this warp has been read out (lane 0 owns the groups)
-        if (lane == 0) ptx::bulk_wait_group_read0();
-        __syncwarp();
-        unsigned char* dst = smem_gen + stg_off + lane * (D * 2);
 #pragma unroll
-        for (int c = 0; c < D / 8; ++c) {
-          __align__(16) __half2 pk[4];
+        for (int ps = 0; ps < C::EPI_NPASS; ++ps) {
+          // the staging tile is free once the previous store of this warp has been read out (lane 0 owns the groups)
+          if (lane == 0) ptx::bulk_wait_group_read0();
+          __syncwarp();
+          unsigned char* dst = smem_gen + stg_off + lane * (C::EPI_CW * 2);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) pk[q] = __floats2half2_rn(o[c * 8 + 2 * q] * inv, o[c * 8 + 2 * q + 1] * inv);
-          reinterpret_cast<uint4*>(dst)[c] = *reinterpret_cast<const uint4*>(pk);
-        }
-        ptx::fence_proxy_async_smem();           // generic-proxy writes -> visible to the TMA (async proxy)
-        __syncwarp();
-        const int n0 = pend_n - lane;            // first row of this warp's 32-row slice; rows >= N are clipped by TMA
-        if (lane == 0 && n0 < p.N) {
-          ptx::tma_store_4d(&tmo, smem0 + stg_off, 0, pend_h, n0, pend_b);
-          ptx::bulk_commit_group();
+          for (int c = 0; c < C::EPI_CW / 8; ++c) {
+            __align__(16) __half2 pk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              pk[q] = __floats2half2_rn(o[ps * C::EPI_CW + c * 8 + 2 * q] * inv, o[ps * C::EPI_CW + c * 8 + 2 * q + 1] * inv);
+            const int cs = C::EPI_SW ? (c ^ (lane & 7)) : c;       // 16-byte chunk position inside the (swizzled) row
+            reinterpret_cast<uint4*>(dst)[cs] = *reinterpret_cast<const uint4*>(pk);
+          }
+          ptx::fence_proxy_async_smem();           // generic-proxy writes -> visible to the TMA (async proxy)
+          __syncwarp();
+          const int n0 = pend_n - lane;            // first row of this warp's 32-row slice; rows >= N are clipped by TMA
+          if (lane == 0 && n0 < p.N) {
+            ptx::tma_store_4d(&tmo, smem0 + stg_off, ps * C::EPI_CW, pend_h, n0, pend_b);
+            ptx::bulk_commit_group();
+          }
         }
       } else {
         if (pend_n < p.N) {
@@ -918,25 +929,26 @@ inline int fwd_schedule_host(int B, int H, int tiles, int grid, const int* wmap_
   return row;
 }
 
-// Forward-kernel epilogue: 1 = TMA stores where they apply (see EPI_TMA on xattn_fwd_tc_kernel), 0 = per-thread global
-// stores everywhere; pww_debug_set_variant overrides it for A/B timing.
+// Forward-kernel structure: 0 = per-thread global stores everywhere, 1 = TMA-store epilogue at D = 40 (default),
+// 2 = experimental four-group kernel at D = 40, 3 = TMA-store epilogue at every head dim (not yet run on hardware for
+// D != 40); pww_debug_set_variant overrides it for A/B timing.
 constexpr int kDefaultFwdVariant = 1;
 inline int& fwd_variant() {
   static int v = kDefaultFwdVariant;
   return v;
 }
-// Row-major [B, L, H, D] fp16 output as a TMA tensor: boxes of [D x 1 x rows x 1], no swizzle.
+// Row-major [B, L, H, D] fp16 output as a TMA tensor: boxes of [box_cols x 1 x rows x 1], plain or 128-byte swizzled.
 inline bool make_tmap_out(CUtensorMap* m, const void* base, int D, int H, int L, int B, int64_t row_stride,
-                          int64_t batch_stride, int box_rows) {
+                          int64_t batch_stride, int box_rows, int box_cols, bool swizzle128) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)H, (cuuint64_t)L, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)D * 2, (cuuint64_t)row_stride * 2, (cuuint64_t)batch_stride * 2};
-  cuuint32_t box[4] = {(cuuint32_t)D, 1, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[4] = {(cuuint32_t)box_cols, 1, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
@@ -980,16 +992,19 @@ cudaError_t launch_fwd(const XattnParams& x, cudaStream_t s) {
   tp.units = x.B * tp.tiles * x.H;
   tp.k_batched = x.k_bs > 0 ? 1 : 0;
   tp.timeline = debug_timeline();
-  // the TMA-store epilogue needs a 16-byte aligned, 16-byte strided output; shared memory has room for its staging
-  // tiles only at D = 40 (the 64x64-latent layers, where this kernel spends its time)
+  // The TMA-store epilogue needs a 16-byte aligned, 16-byte strided output.  It is the default at D = 40 (the 64x64-latent
+  // layers, where this kernel spends its time; verified and A/B-timed on hardware); for the other head dims it is built
+  // but only selected by variant 3 until it has been through the parity tests on a GPU.
   CUtensorMap to = tq;
-  if constexpr (D == 40) {
-    const bool tma_ok = (reinterpret_cast<uintptr_t>(x.out) & 15u) == 0 && (x.o_rs * 2) % 16 == 0 &&
-                        (x.o_bs * 2) % 16 == 0 && x.o_bs > 0;
-    if (fwd_variant() >= 1 && tma_ok && make_tmap_out(&to, x.out, D, x.H, x.N, x.B, x.o_rs, x.o_bs, 32)) {
-      if (fwd_variant() == 2) return launch_fwd_g4(tq, tk, tv, to, tp, s);   // experimental, see xattn_tc_g4.cuh
-      return launch_fwd_var<D, true>(tq, tk, tv, to, tp, s);
+  const int var = fwd_variant();
+  const bool want = (D == 40) ? (var >= 1) : (var == 3);
+  const bool tma_ok = (reinterpret_cast<uintptr_t>(x.out) & 15u) == 0 && (x.o_rs * 2) % 16 == 0 &&
+                      (x.o_bs * 2) % 16 == 0 && x.o_bs > 0;
+  if (want && tma_ok && make_tmap_out(&to, x.out, D, x.H, x.N, x.B, x.o_rs, x.o_bs, 32, C::EPI_CW, C::EPI_SW)) {
+    if constexpr (D == 40) {
+      if (var == 2) return launch_fwd_g4(tq, tk, tv, to, tp, s);   // experimental, see xattn_tc_g4.cuh
     }
+    return launch_fwd_var<D, true>(tq, tk, tv, to, tp, s);
   }
   return launch_fwd_var<D, false>(tq, tk, tv, to, tp, s);
 }
