@@ -312,9 +312,10 @@ int pww_debug_set_timeline(void* device_buffer) {
 
 // Test infrastructure (not declared in the public header): structure of the tcgen05 forward kernel, for A/B timing.
 // 0 = per-thread global stores, 1 = TMA-store epilogue at D = 40 (default), 2 = experimental four-group kernel at
-// D = 40 (xattn_tc_g4.cuh), 3 = TMA-store epilogue at every head dim (see xattn_tc.cuh).
+// D = 40 (xattn_tc_g4.cuh), 3 = TMA-store epilogue at every head dim, 4 = variant 2's code with two groups
+// (see xattn_tc.cuh).
 int pww_debug_set_variant(int variant) {
-  if (variant < 0 || variant > 3) return PWW_ERR_BAD_ARG;
+  if (variant < 0 || variant > 4) return PWW_ERR_BAD_ARG;
   pww::tc::fwd_variant() = variant;
   return PWW_OK;
 }

@@ -931,7 +931,8 @@ inline int fwd_schedule_host(int B, int H, int tiles, int grid, const int* wmap_
 
 // Forward-kernel structure: 0 = per-thread global stores everywhere, 1 = TMA-store epilogue at D = 40 (default),
 // 2 = experimental four-group kernel at D = 40, 3 = TMA-store epilogue at every head dim (not yet run on hardware for
-// D != 40); pww_debug_set_variant overrides it for A/B timing.
+// D != 40), 4 = the four-group kernel's code built with two groups (bisection point); pww_debug_set_variant overrides
+// it for A/B timing.
 constexpr int kDefaultFwdVariant = 1;
 inline int& fwd_variant() {
   static int v = kDefaultFwdVariant;
@@ -953,7 +954,7 @@ inline bool make_tmap_out(CUtensorMap* m, const void* base, int D, int H, int L,
 }
 
 cudaError_t launch_fwd_g4(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
-                          const TcParams& tp, cudaStream_t s);   // xattn_tc_g4.cuh
+                          const TcParams& tp, cudaStream_t s, int groups);   // xattn_tc_g4.cuh
 
 template <int D, bool EPI_TMA>
 cudaError_t launch_fwd_var(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
@@ -997,12 +998,12 @@ cudaError_t launch_fwd(const XattnParams& x, cudaStream_t s) {
   // but only selected by variant 3 until it has been through the parity tests on a GPU.
   CUtensorMap to = tq;
   const int var = fwd_variant();
-  const bool want = (D == 40) ? (var >= 1) : (var == 3);
+  const bool want = (D == 40) ? (var >= 1) : (var == 3);       // (variants 2 and 4 only exist at D = 40)
   const bool tma_ok = (reinterpret_cast<uintptr_t>(x.out) & 15u) == 0 && (x.o_rs * 2) % 16 == 0 &&
                       (x.o_bs * 2) % 16 == 0 && x.o_bs > 0;
   if (want && tma_ok && make_tmap_out(&to, x.out, D, x.H, x.N, x.B, x.o_rs, x.o_bs, 32, C::EPI_CW, C::EPI_SW)) {
     if constexpr (D == 40) {
-      if (var == 2) return launch_fwd_g4(tq, tk, tv, to, tp, s);   // experimental, see xattn_tc_g4.cuh
+      if (var == 2 || var == 4) return launch_fwd_g4(tq, tk, tv, to, tp, s, var == 2 ? 4 : 2);   // experimental
     }
     return launch_fwd_var<D, true>(tq, tk, tv, to, tp, s);
   }

@@ -26,8 +26,7 @@ namespace tc {
 namespace g4 {
 
 constexpr int kD = 40;
-constexpr int kG = 4;                      // softmax groups
-constexpr int kThreads4 = 128 + kG * 128;  // 640
+constexpr int kGMax = 4;                   // softmax groups (the kernel is also built with 2, as a bisection point)
 constexpr int NQK = 3, NV = 4;
 constexpr uint32_t QKSTAGE = kQAtom + kKAtom;       // one 64-column atom each (D = 40)
 constexpr uint32_t VSTAGE = kKAtom;
@@ -36,7 +35,7 @@ constexpr uint32_t OFF_MASK = OFF_V + NV * VSTAGE;
 constexpr uint32_t OFF_BAR = OFF_MASK + kMaskBytes;
 constexpr uint32_t OFF_STG = OFF_BAR + 256;
 constexpr uint32_t STG_WARP = 32 * kD * 2;
-constexpr uint32_t SMEM = OFF_STG + kG * 4 * STG_WARP + 1024;
+constexpr uint32_t SMEM = OFF_STG + kGMax * 4 * STG_WARP + 1024;
 static_assert(SMEM + 8192 <= 232448, "shared memory budget (dynamic + static tables)");
 static_assert(OFF_STG % 128 == 0 && QKSTAGE % 1024 == 0 && OFF_V % 1024 == 0, "TMA / swizzle alignment");
 constexpr int DPV = 48;                    // UMMA N of P.V: 40 value columns + the ones column, padded to 16
@@ -44,10 +43,10 @@ constexpr int DPV = 48;                    // UMMA N of P.V: 40 value columns + 
 // at a 16-column aligned offset (the verified D = 80 kernel keeps S at columns 80 and 240).
 __host__ __device__ constexpr uint32_t col_o(int g) { return 128u * g; }
 __host__ __device__ constexpr uint32_t col_s(int g) { return 128u * g + 48u; }
-static_assert(col_s(kG - 1) + kTP <= 512, "TMEM budget");
+static_assert(col_s(kGMax - 1) + kTP <= 512, "TMEM budget");
 
-template <int TT>
-__global__ void __launch_bounds__(kThreads4, 1)
+template <int TT, int kG>
+__global__ void __launch_bounds__(128 + kG * 128, 1)
 xattn_fwd_g4_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
                     const __grid_constant__ CUtensorMap tmv, const __grid_constant__ CUtensorMap tmo,
                     const TcParams tp) {
@@ -61,6 +60,7 @@ xattn_fwd_g4_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   // the group) is behind SREADY of that unit, which is behind PVDONE of this one, which is behind this phase.
   constexpr int B_QFULL = 0, B_QEMPTY = 3, B_VFULL = 6, B_VEMPTY = 10, B_MFULL = 14, B_MEMPTY = 15, B_SREADY = 16,
                 B_PREADY = 20, B_PVDONE = 24, B_TMEMPTR = 28;
+  constexpr int kThreads4 = 128 + kG * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int u0, u1;
   cta_range(tp.units, u0, u1);
@@ -360,22 +360,29 @@ xattn_fwd_g4_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
 
 }  // namespace g4
 
-inline cudaError_t launch_fwd_g4(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-                                 const CUtensorMap& to, const TcParams& tp, cudaStream_t s) {
+template <int G>
+cudaError_t launch_fwd_g4_impl(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                               const CUtensorMap& to, const TcParams& tp, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(g4::xattn_fwd_g4_kernel<77>, cudaFuncAttributeMaxDynamicSharedMemorySize, g4::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(g4::xattn_fwd_g4_kernel<77, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, g4::SMEM);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(g4::xattn_fwd_g4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, g4::SMEM);
+      e = cudaFuncSetAttribute(g4::xattn_fwd_g4_kernel<0, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, g4::SMEM);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   const int grid = tp.units < num_sms() ? tp.units : num_sms();
   if (tp.x.T == 77)
-    g4::xattn_fwd_g4_kernel<77><<<grid, g4::kThreads4, g4::SMEM, s>>>(tq, tk, tv, to, tp);
+    g4::xattn_fwd_g4_kernel<77, G><<<grid, 128 + G * 128, g4::SMEM, s>>>(tq, tk, tv, to, tp);
   else
-    g4::xattn_fwd_g4_kernel<0><<<grid, g4::kThreads4, g4::SMEM, s>>>(tq, tk, tv, to, tp);
+    g4::xattn_fwd_g4_kernel<0, G><<<grid, 128 + G * 128, g4::SMEM, s>>>(tq, tk, tv, to, tp);
   return cudaGetLastError();
 }
+// groups = 4: the design point; groups = 2: the same code with the thread count of the shipped kernel (bisection)
+inline cudaError_t launch_fwd_g4(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                                 const CUtensorMap& to, const TcParams& tp, cudaStream_t s, int groups) {
+  return groups == 2 ? launch_fwd_g4_impl<2>(tq, tk, tv, to, tp, s) : launch_fwd_g4_impl<4>(tq, tk, tv, to, tp, s);
+}
+
 }  // namespace tc
 }  // namespace pww
