@@ -7,6 +7,8 @@
 //   B. May TWO warps issue tcgen05.mma chains concurrently -- each warp both an SS-form chain (A from shared memory)
 //      and a TS-form chain (A from tensor memory)?  The shipped kernels issue all SS chains from one warp and all TS
 //      chains from another (fine); a variant where each of two warps issued both gave wrong results.
+//   C. The other two things the four-group kernel does that no verified kernel does: a 20-warp CTA whose warps 16-19 use
+//      tcgen05.ld / tcgen05.st, and an fp32 tcgen05.st write-back into an accumulator that is then re-loaded.
 //
 // build:  nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -I paint_with_words_sd_b200/csrc \
 //              -o scripts/bin/umma_probe scripts/umma_probe.cu
@@ -36,13 +38,14 @@ struct Case {
   int mode;        // 0: single issuer, SS chain into column d0 | 1: single issuer, TS chain (A = fp16 pairs stored at a0)
                    // 2: two warps, each issues an SS chain then a TS chain, concurrently | 3: the same work from ONE
                    // warp (control) | 4: the shipped pattern: one warp issues both SS chains, another both TS chains
+                   // 5: mode 0 in a 640-thread CTA, checked by warps 16-19 after a tcgen05.st write-back (+1) and re-load
   int n;           // UMMA N (multiple of 16)
   int d0, a0;      // accumulator column / TS-form A column of chain 0
   int d1, a1;      // same for chain 1 (modes 2, 3)
   int rounds;
 };
 
-__global__ void __launch_bounds__(192, 1) probe_kernel(Case cs, int* errors) {
+__global__ void __launch_bounds__(640, 1) probe_kernel(Case cs, int* errors) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   unsigned char* smem = smem_raw + (smem0 - ptx::smem_u32(smem_raw));
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(192, 1) probe_kernel(Case cs, int* errors) {
       for (int ks = 0; ks < kKS; ++ks)
         ptx::umma_ts(tmem + dcol, tmem + acol + ks * 8, ptx::make_sw128_desc(smem0 + offB[c] + ks * 32, 16, 1024), idesc, ks > 0);
     };
-    if (cs.mode == 0 && warp == 4 && lane == 0) { ss_chain(0, cs.d0); ptx::umma_commit(BAR(0)); }
+    if ((cs.mode == 0 || cs.mode == 5) && warp == 4 && lane == 0) { ss_chain(0, cs.d0); ptx::umma_commit(BAR(0)); }
     if (cs.mode == 1 && warp == 4 && lane == 0) { ts_chain(0, cs.d0, cs.a0); ptx::umma_commit(BAR(0)); }
     if (cs.mode == 2 && (warp == 4 || warp == 5) && lane == 0) {
       // each warp: SS chain into its first accumulator, TS chain into its second one (d + n rounded up to 16 apart)
@@ -123,9 +126,10 @@ __global__ void __launch_bounds__(192, 1) probe_kernel(Case cs, int* errors) {
       ptx::umma_commit(BAR(1));
     }
     // ---- check
-    if (warp < 4) {
-      const int row = warp * 32 + lane;
-      const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const int rbase = cs.mode == 5 ? 16 : 0;       // which four warps read the accumulators back
+    if (warp >= rbase && warp < rbase + 4) {
+      const int row = (warp - rbase) * 32 + lane;
+      const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
       for (int c = 0; c < chains; ++c) ptx::mbar_wait(BAR(c), (uint32_t)(round & 1));
       ptx::tc_fence_after();
       for (int c = 0; c < chains; ++c) {
@@ -136,6 +140,13 @@ __global__ void __launch_bounds__(192, 1) probe_kernel(Case cs, int* errors) {
           for (int n0 = 0; n0 < cs.n; n0 += 16) {
             float v[16];
             ptx::tmem_ld16_sync(tmem + lane_addr + dcol + n0, v);
+            if (cs.mode == 5) {                      // write-back and re-load, like pass 1 -> pass 2 of the softmax
+              for (int j = 0; j < 16; ++j) v[j] += 1.0f;
+              ptx::tmem_st16(tmem + lane_addr + dcol + n0, v);
+              ptx::tmem_st_wait();
+              ptx::tmem_ld16_sync(tmem + lane_addr + dcol + n0, v);
+              for (int j = 0; j < 16; ++j) v[j] -= 1.0f;
+            }
             for (int j = 0; j < 16; ++j) {
               int ref = 0;
               for (int k = 0; k < K; ++k)
@@ -170,10 +181,12 @@ int main() {
       // (accumulators of chain c: SS at d, TS at d + 128; TS-form A operands in the gaps)
       {3, 80, 0, 208, 256, 464, 64}, {4, 80, 0, 208, 256, 464, 64}, {2, 80, 0, 208, 256, 464, 64},
       {2, 48, 0, 208, 256, 464, 64},
+      // C: 20-warp CTA, accumulators read / written back / re-read by warps 16-19
+      {5, 80, 48, 0, 0, 0, 4}, {5, 80, 432, 0, 0, 0, 4}, {5, 48, 384, 0, 0, 0, 4},
   };
   for (const Case& c : cases) {
     cudaMemset(d_err, 0, sizeof(int));
-    probe_kernel<<<1, 192, smem>>>(c, d_err);
+    probe_kernel<<<1, c.mode == 5 ? 640 : 192, smem>>>(c, d_err);
     cudaError_t e = cudaDeviceSynchronize();
     int h = -1;
     if (e == cudaSuccess) cudaMemcpy(&h, d_err, sizeof(int), cudaMemcpyDeviceToHost);
