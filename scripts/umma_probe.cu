@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(640, 1) probe_kernel(Case cs, int* errors) {
         if (r < cs.n) *reinterpret_cast<__half*>(smem + offB[c] + sw128_off(r, k)) = __int2half_rn(b_val(r, k, 11 * c + round));
       }
     // TS-form A operand: row = lane, 32-bit column j holds K elements 2j, 2j+1 (K/2 columns)
-    if (warp < 4 && cs.mode >= 1) {
+    if (warp < 4 && cs.mode >= 1 && cs.mode <= 4) {
       const int row = warp * 32 + lane;
       const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
       for (int c = 0; c < chains; ++c) {
