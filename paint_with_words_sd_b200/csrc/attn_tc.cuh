@@ -189,11 +189,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     __syncwarp();
   } else if (warp == 3) {
     // ------------------------------------------------ UMMA issuer: O_g += P_g V_j
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_f16(128, C::DPV, false, true);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j % C::NV;
-        ptx::mbar_wait(BAR(B_VFULL + st), (uint32_t)((j / C::NV) & 1));
+    // The whole warp waits for the V tile (every VFULL phase is observed by the same threads, in order) and, for
+    // D = 40 / 80, sets the spare column of the last V atom to 1.0 for every real key: accumulator column D of the
+    // P.V UMMA is then the row sum of the fp16 P that was multiplied.
+    constexpr uint32_t idesc = ptx::make_idesc_f16(128, C::DPV, false, true);
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j % C::NV;
+      ptx::mbar_wait(BAR(B_VFULL + st), (uint32_t)((j / C::NV) & 1));
+      if constexpr (C::ONES) {
+        const int valid = p.N - j * C::BN;          // keys of this tile that exist
+        unsigned char* vlast = smem_gen + C::OFF_V + st * C::VSTAGE + (C::NA - 1) * C::KATOM;
+        constexpr int cc = D % 64;
+        for (int r = lane; r < C::BN && r < valid; r += 32)
+          *reinterpret_cast<__half*>(vlast + r * 128 + ((((cc >> 3) ^ (r & 7))) << 4) + (cc & 7) * 2) = __float2half(1.0f);
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+      }
+      if (lane == 0) {
         for (int g = 0; g < nq_live; ++g) {
           const int pb = j % C::NP;
           ptx::mbar_wait(BAR(B_PREADY + g * 2 + pb), (uint32_t)((j / C::NP) & 1));
@@ -207,8 +219,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         }
         ptx::umma_commit(BAR(B_VEMPTY + st));
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     // ------------------------------------------------ softmax groups
     const int g = (warp >> 2) - 1;
@@ -291,18 +303,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
           ptx::tmem_st16_u32(tmem_base + lane_addr + C::col_p(g, pbuf) + c0 / 2, pk);   // 32 fp16 = 16 columns of P
         }
         ptx::tmem_st_wait();
-        if constexpr (C::ONES) {
-          // key r = this thread's row index: V[r][D] = 1.0 in the last V atom -> accumulator column D = row sum of P
-          ptx::mbar_wait(BAR(B_VFULL + j % C::NV), (uint32_t)((j / C::NV) & 1));
-          if (row < C::BN && row < valid) {
-            unsigned char* vlast = smem_gen + C::OFF_V + (j % C::NV) * C::VSTAGE + (C::NA - 1) * C::KATOM;
-            constexpr int cc = D % 64;
-            *reinterpret_cast<__half*>(vlast + row * 128 + ((((cc >> 3) ^ (row & 7))) << 4) + (cc & 7) * 2) =
-                __float2half(1.0f);
-          }
-        } else {
-          l_run = l_run * factor + ((a0 + a1) + (a2 + a3));
-        }
+        if constexpr (!C::ONES) l_run = l_run * factor + ((a0 + a1) + (a2 + a3));
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
         __syncwarp();

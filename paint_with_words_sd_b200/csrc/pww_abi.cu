@@ -3,9 +3,7 @@
 #include <string.h>
 
 #include "pww_common.cuh"
-#include "xattn_simt.cuh"
 #include "xattn_tc.cuh"
-#include "xattn_tc_g4.cuh"
 #include "attn_tc.cuh"
 #include "unet_ops.cuh"
 #include <stdlib.h>
@@ -26,61 +24,15 @@ int check_common(const void* q, const void* k, int B, int H, int N, int T, int D
   if (!aligned16(q) || !aligned16(k)) return PWW_ERR_BAD_ARG;
   if ((q_bs | q_rs | k_bs | k_rs) & 7) return PWW_ERR_BAD_ARG;  // 16-byte vector access on rows
   if (q_rs < (int64_t)H * D || k_rs < (int64_t)H * D) return PWW_ERR_BAD_ARG;
-  if (!supported_head_dim(D) || T > 128) return PWW_ERR_UNSUPPORTED;
+  if (!supported_head_dim(D) || T > pww::tc::kTP) return PWW_ERR_UNSUPPORTED;
   return PWW_OK;
 }
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-int stats_ctas_per_image(int H, int N) { return H * pww::ceil_div(N, pww::simt::kRows); }
-
-// Partial slots reserved per image: covers the tcgen05 kernel (8 reducer warps x <=256 SMs) and the CUDA-core
-// kernel (one slot per CTA of the image).  Device independent so the size can be computed without a GPU.
-int stats_slots_per_image(int H, int N) {
-  int simt = stats_ctas_per_image(H, N);
-  return simt > 2048 ? simt : 2048;
-}
-
-// tcgen05 path covers the Stable Diffusion key lengths (T <= 80); 81..128 keys run on the CUDA-core kernels.
-bool use_tc(int T) {
-  static int force_simt = -1;
-  if (force_simt < 0) {
-    const char* e = getenv("PWW_FORCE_SIMT");
-    force_simt = (e && e[0] == '1') ? 1 : 0;
-  }
-  return T <= pww::tc::kTP && !force_simt;
-}
-
-template <typename K>
-int set_smem(K kernel, size_t bytes) {
-  if (bytes > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) return cuda_fail(e);
-  }
-  return PWW_OK;
-}
-
-template <int D>
-int launch_stats(const pww::XattnParams& p, cudaStream_t s) {
-  size_t smem = pww::simt::stats_smem(p.T, D);
-  int rc = set_smem(pww::simt::xattn_stats_kernel<D>, smem);
-  if (rc) return rc;
-  dim3 grid(pww::ceil_div(p.N, pww::simt::kRows), p.H, p.B);
-  pww::simt::xattn_stats_kernel<D><<<grid, pww::simt::kRows, smem, s>>>(p);
-  cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? PWW_OK : cuda_fail(e);
-}
-
-template <int D>
-int launch_fwd(const pww::XattnParams& p, cudaStream_t s) {
-  size_t smem = pww::simt::fwd_smem(p.T, D);
-  int rc = set_smem(pww::simt::xattn_fwd_kernel<D>, smem);
-  if (rc) return rc;
-  dim3 grid(pww::ceil_div(p.N, pww::simt::kRows), p.H, p.B);
-  pww::simt::xattn_fwd_kernel<D><<<grid, pww::simt::kRows, smem, s>>>(p);
-  cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? PWW_OK : cuda_fail(e);
-}
+// Partial slots reserved per image (one per CTA of the persistent grid; device independent upper bound so the size
+// can be computed without a GPU).
+int stats_slots_per_image(int, int) { return 2048; }
 
 int cuda_fail(cudaError_t e) {
   snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s %s", cudaGetErrorName(e), cudaGetErrorString(e),
@@ -99,7 +51,7 @@ const char* pww_status_str(int status) {
   switch (status) {
     case PWW_OK: return "ok";
     case PWW_ERR_BAD_ARG: return "bad argument (null/misaligned pointer, non-positive size or stride not a multiple of 8)";
-    case PWW_ERR_UNSUPPORTED: return "unsupported shape (head dim must be 40/64/80/160, T <= 128)";
+    case PWW_ERR_UNSUPPORTED: return "unsupported shape (head dim must be 40/64/80/160, T <= 80)";
     case PWW_ERR_CUDA: return "CUDA error (see pww_last_cuda_error)";
     case PWW_ERR_WORKSPACE: return "workspace too small (see pww_xattn_workspace_bytes)";
     default: return "unknown status";
@@ -140,9 +92,8 @@ int pww_xattn_stats_f16(const void* q, const void* k, int B, int H, int N, int T
   p.wmap_index = wmap_index; p.stat = stat; p.stats_out = stats;
   p.counters = (unsigned int*)workspace;
   p.partials = (pww::StatPartial*)((char*)workspace + align_up((size_t)B * sizeof(unsigned int), 256));
-  p.ctas_per_image = stats_ctas_per_image(H, N);
   cudaStream_t s = (cudaStream_t)stream;
-  if (use_tc(T)) {
+  {
     if (pww::tc::stats_slots() > stats_slots_per_image(H, N)) return PWW_ERR_WORKSPACE;
     for (int b0 = 0; b0 < B; b0 += pww::tc::kMaxBatch) {          // <= 256 images per launch
       pww::XattnParams c = p;
@@ -162,13 +113,6 @@ int pww_xattn_stats_f16(const void* q, const void* k, int B, int H, int N, int T
     }
     return PWW_OK;
   }
-  switch (D) {
-    case 40: return launch_stats<40>(p, s);
-    case 64: return launch_stats<64>(p, s);
-    case 80: return launch_stats<80>(p, s);
-    case 160: return launch_stats<160>(p, s);
-  }
-  return PWW_ERR_UNSUPPORTED;
 }
 
 int pww_xattn_fwd_f16(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int T, int D,
@@ -190,7 +134,7 @@ int pww_xattn_fwd_f16(const void* q, const void* k, const void* v, void* out, in
   p.wmap = wmap; p.wmap_bs = wmap_batch_stride; p.wmap_index = wmap_index;
   p.stats = stats; p.g_sigma = g_sigma; p.scale = scale;
   cudaStream_t s = (cudaStream_t)stream;
-  if (use_tc(T)) {
+  {
     for (int b0 = 0; b0 < B; b0 += pww::tc::kMaxBatch) {          // <= 256 images per launch
       pww::XattnParams c = p;
       c.B = (B - b0) < pww::tc::kMaxBatch ? (B - b0) : pww::tc::kMaxBatch;
@@ -212,13 +156,6 @@ int pww_xattn_fwd_f16(const void* q, const void* k, const void* v, void* out, in
     }
     return PWW_OK;
   }
-  switch (D) {
-    case 40: return launch_fwd<40>(p, s);
-    case 64: return launch_fwd<64>(p, s);
-    case 80: return launch_fwd<80>(p, s);
-    case 160: return launch_fwd<160>(p, s);
-  }
-  return PWW_ERR_UNSUPPORTED;
 }
 
 size_t pww_groupnorm_workspace_bytes(int B, int HW, int G) {
@@ -311,11 +248,10 @@ int pww_debug_set_timeline(void* device_buffer) {
 }
 
 // Test infrastructure (not declared in the public header): structure of the tcgen05 forward kernel, for A/B timing.
-// 0 = per-thread global stores, 1 = TMA-store epilogue at D = 40 (default), 2 = experimental four-group kernel at
-// D = 40 (xattn_tc_g4.cuh), 3 = TMA-store epilogue at every head dim, 4 = variant 2's code with two groups
+// 0 = per-thread global stores, 1 = TMA-store epilogue at D = 40 (default), 3 = TMA-store epilogue at every head dim
 // (see xattn_tc.cuh).
 int pww_debug_set_variant(int variant) {
-  if (variant < 0 || variant > 4) return PWW_ERR_BAD_ARG;
+  if (variant != 0 && variant != 1 && variant != 3) return PWW_ERR_BAD_ARG;
   pww::tc::fwd_variant() = variant;
   return PWW_OK;
 }

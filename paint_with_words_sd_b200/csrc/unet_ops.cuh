@@ -85,8 +85,10 @@ __global__ void gn_stats_kernel(GnParams p) {
   __syncthreads();
   if (!is_last) return;
   __threadfence();
+  // only FULL warps finalise (blockDim.x = nvec * rpp need not be a multiple of 32: a trailing partial warp would
+  // alias warp 0's groups and shuffle with lanes that do not exist)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int g = warp; g < p.G; g += nwarps) {
+  for (int g = warp; warp < nwarps && g < p.G; g += nwarps) {
     const float* pp = p.partial + ((size_t)b * p.chunks * p.G + g) * 2;
     float ts = 0.f, tq = 0.f;
     for (int c = lane; c < p.chunks; c += 32) { ts += __ldcg(pp + (size_t)c * p.G * 2); tq += __ldcg(pp + (size_t)c * p.G * 2 + 1); }

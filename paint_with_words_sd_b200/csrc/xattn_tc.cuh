@@ -206,6 +206,10 @@ __host__ __device__ __forceinline__ int mask_release_pos(const FwdUnit& f, int i
   if (j_hi > f.gsize - 1) j_hi = f.gsize - 1;
   return (f.jl >= j_lo && f.jl <= j_hi) ? f.jl : j_hi;
 }
+// Mask-barrier rule (shared by the kernel and the host replay): EVERY softmax warp waits for B_MFULL at the first unit
+// of each mask group of its CTA, whether or not it reads the tile.  A warp therefore observes the phases of B_MFULL
+// in order 0, 1, 2, ... and a parity wait can never be satisfied by a phase it skipped.
+__host__ __device__ __forceinline__ bool mask_group_starts_here(const FwdUnit& f, int it) { return f.j == 0 || it == 0; }
 __device__ __forceinline__ void cta_range(int units, int& u0, int& u1) {
   u0 = (int)((long long)blockIdx.x * units / gridDim.x);
   u1 = (int)((long long)(blockIdx.x + 1) * units / gridDim.x);
@@ -365,13 +369,14 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       }
       __syncwarp();
     }
-  } else if (warp == 1 || warp == 11) {
-    // ===================================== UMMA issuers =====================================
+  } else if (warp == 1) {
+    // ===================================== UMMA issuer: S = Q K^T of every unit, in unit order =====================================
+    // (One issuer warp per softmax group -- each issuing its group's S and P.V -- was tried and gave wrong results at
+    //  D = 64: see profiles/.  Warp 1 issues every SS-form chain, warp 11 every TS-form chain.)
     if (lane == 0) {
       constexpr uint32_t idesc_qk = ptx::make_idesc_f16(128, kTP, false, false);
-      constexpr uint32_t idesc_pv = ptx::make_idesc_f16(128, C::DPV, false, true);
-      // S[g][buf] = Q K^T of unit `it` (the group's unit `local`)
-      auto issue_qk = [&](int it) {
+      for (int it = 0; it < n_it; ++it) {
+        // S[g][buf] = Q K^T of unit `it` (the group's unit `local`)
         const int st = it % C::NQK, g = it & 1, local = it >> 1, buf = local % C::NSB, k = local / C::NSB;
         ptx::mbar_wait(BAR(B_QFULL + st), (uint32_t)((it / C::NQK) & 1));
         if (k >= 1)                                      // the P.V that read P out of this buffer has finished
@@ -389,13 +394,30 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         ptx::umma_commit(BAR(B_SREADY + g * 2 + buf));
         ptx::umma_commit(BAR(B_QEMPTY + st));      // Q/K tiles are dead once S exists
         PWW_TL(4, it);
-      };
-      // O[g] = P V of unit `j`; P is read from the score buffer it overwrote
-      auto issue_pv = [&](int j) {
-        const int st = j % C::NV, g = j & 1, local = j >> 1, buf = local % C::NSB, k = local / C::NSB;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 11) {
+    // ===================================== UMMA issuer: O = P V of every unit, in unit order =====================================
+    // The whole warp waits for the V tile (so every VFULL phase of every stage is observed by the same threads, in
+    // order) and, for D = 40 / 80, sets the spare column of the last V atom to 1.0 for every real token: accumulator
+    // column D of the P.V UMMA is then the row sum of the fp16 P that was multiplied.
+    constexpr uint32_t idesc_pv = ptx::make_idesc_f16(128, C::DPV, false, true);
+    for (int j = 0; j < n_it; ++j) {
+      const int st = j % C::NV, g = j & 1, local = j >> 1, buf = local % C::NSB, k = local / C::NSB;
+      ptx::mbar_wait(BAR(B_VFULL + st), (uint32_t)((j / C::NV) & 1));
+      if constexpr (C::ONES) {
+        unsigned char* vlast = smem_gen + C::OFF_V + st * C::VSTAGE + (C::NA - 1) * kKAtom;
+        constexpr int cc = D % 64;                 // spare column inside the last atom
+        for (int r = lane; r < (TT ? TT : p.T); r += 32)
+          *reinterpret_cast<__half*>(vlast + r * 128 + ((((cc >> 3) ^ (r & 7))) << 4) + (cc & 7) * 2) = __float2half(1.0f);
+        ptx::fence_proxy_async_smem();             // generic-proxy writes -> visible to the UMMA (async proxy)
+        __syncwarp();
+      }
+      if (lane == 0) {
+        // O[g] = P V of unit `j`; P is read from the score buffer it overwrote
         ptx::mbar_wait(BAR(B_PREADY + g * 2 + buf), (uint32_t)(k & 1));
         if (local >= 1) ptx::mbar_wait(BAR(B_OFREE + g), (uint32_t)((local - 1) & 1));
-        ptx::mbar_wait(BAR(B_VFULL + st), (uint32_t)((j / C::NV) & 1));
         PWW_TL(3, j);
         ptx::tc_fence_after();
         const uint32_t vb = smem0 + C::OFF_V + st * C::VSTAGE;
@@ -406,16 +428,9 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         ptx::umma_commit(BAR(B_PVDONE + g * 2 + buf));
         ptx::umma_commit(BAR(B_VEMPTY + st));
         PWW_TL(8, j);
-      };
-      // warp 1 issues every S = Q K^T, warp 11 every O = P V, both in unit order.  (One issuer warp per softmax group
-      // -- each issuing its group's S and P.V -- was tried and gave wrong results at D = 64: see profiles/.)
-      if (warp == 1) {
-        for (int it = 0; it < n_it; ++it) issue_qk(it);
-      } else {
-        for (int j = 0; j < n_it; ++j) issue_pv(j);
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     // ===================================== softmax / epilogue groups =====================================
     const int g = (warp - 2) >> 2;
@@ -488,7 +503,11 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
 
     for (int it = 0; it < n_it; ++it, ws.next()) {
       const FwdUnit ui = ws.get();
-      if (ui.j == 0 || it == 0) ++grp;
+      if (mask_group_starts_here(ui, it)) {
+        // all 8 softmax warps, both groups: observe this group's MFULL phase before any read or release of the tile
+        ++grp;
+        ptx::mbar_wait(BAR(B_MFULL), (uint32_t)(grp & 1));
+      }
       // every softmax warp releases the group's mask tile exactly once, at this position of the group
       const bool release_here = (ui.j == mask_release_pos(ui, it, n_it));
       if ((it & 1) == g) {
@@ -504,9 +523,7 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         ptx::tmem_ld16_sync(ts + 64, s + 64);
         if ((threadIdx.x & 127) == 64) PWW_TL(0, it);
         // logits t_j = S_j + coef*w_j (unscaled), row max with 4 independent chains
-        if (widx >= 0) {
-          ptx::mbar_wait(BAR(B_MFULL), (uint32_t)(grp & 1));
-
+        if (widx >= 0) {                            // (this group's MFULL phase was observed at the group's first unit)
           if constexpr (TT == 77) {
 #pragma unroll
             for (int j = 0; j < 77; ++j) s[j] = fmaf(coef, mask_row[j], s[j]);
@@ -547,16 +564,6 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
           }
         }
         const float sum = a0 + a1;
-        if constexpr (C::ONES) {
-          // token r = this thread's row index: V[r][D] = 1.0 in the last V atom of this iteration's stage
-          ptx::mbar_wait(BAR(B_VFULL + it % C::NV), (uint32_t)((it / C::NV) & 1));   // V tile has landed
-          if (row < (TT ? TT : p.T)) {
-            unsigned char* vlast = smem_gen + C::OFF_V + (it % C::NV) * C::VSTAGE + (C::NA - 1) * kKAtom;
-            constexpr int cc = D % 64;             // spare column inside the last atom
-            *reinterpret_cast<__half*>(vlast + row * 128 + ((((cc >> 3) ^ (row & 7))) << 4) + (cc & 7) * 2) =
-                __float2half(1.0f);
-          }
-        }
         if (lane == 0) { const int qd = warp & 3; PWW_TL((qd == 2 ? 7 : (qd == 3 ? 9 : (qd == 0 ? 10 : 11))), it); }
         // P row (packed fp16) over the S row it came from: this thread has the whole row in registers
         ptx::tmem_st32_u32(ts, pk);
@@ -901,8 +908,9 @@ inline long long*& debug_timeline() {
   return ptr;
 }
 // Host replay of the forward kernel's unit schedule (test infrastructure): the same FwdWalk / cta_range /
-// mask_release_pos code the kernel runs, executed on the CPU.  out[u] = {cta, it, b, h, tile, group_id, mask_b,
-// releases_mask_here} for every unit in launch order of each CTA.
+// mask_release_pos / mask_group_starts_here code the kernel runs, executed on the CPU.  out[u] = {cta, it, b, h, tile,
+// group_id, mask_b, flags} for every unit in launch order of each CTA; flags bit 0 = every softmax warp releases the
+// mask tile at this unit, bit 1 = every softmax warp (both groups) waits for B_MFULL at this unit.
 inline int fwd_schedule_host(int B, int H, int tiles, int grid, const int* wmap_index, int* out) {
   if (B <= 0 || B > kMaxBatch || H <= 0 || tiles <= 0 || grid <= 0) return -1;
   int img[kMaxBatch];
@@ -923,16 +931,14 @@ inline int fwd_schedule_host(int B, int H, int tiles, int grid, const int* wmap_
       if (f.j == 0 || it == 0) ++grp;
       int* o = out + 8 * (row++);
       o[0] = cta; o[1] = it; o[2] = f.b; o[3] = f.h; o[4] = f.tile; o[5] = grp; o[6] = f.mask_b;
-      o[7] = (f.j == mask_release_pos(f, it, n_it)) ? 1 : 0;
+      o[7] = ((f.j == mask_release_pos(f, it, n_it)) ? 1 : 0) | (mask_group_starts_here(f, it) ? 2 : 0);
     }
   }
   return row;
 }
 
-// Forward-kernel structure: 0 = per-thread global stores everywhere, 1 = TMA-store epilogue at D = 40 (default),
-// 2 = experimental four-group kernel at D = 40, 3 = TMA-store epilogue at every head dim (not yet run on hardware for
-// D != 40), 4 = the four-group kernel's code built with two groups (bisection point); pww_debug_set_variant overrides
-// it for A/B timing.
+// Forward-kernel epilogue: 0 = per-thread global stores everywhere, 1 = TMA-store epilogue at D = 40 (default),
+// 3 = TMA-store epilogue at every head dim; pww_debug_set_variant overrides it for A/B timing.
 constexpr int kDefaultFwdVariant = 1;
 inline int& fwd_variant() {
   static int v = kDefaultFwdVariant;
@@ -952,9 +958,6 @@ inline bool make_tmap_out(CUtensorMap* m, const void* base, int D, int H, int L,
                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
-
-cudaError_t launch_fwd_g4(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
-                          const TcParams& tp, cudaStream_t s, int groups);   // xattn_tc_g4.cuh
 
 template <int D, bool EPI_TMA>
 cudaError_t launch_fwd_var(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
@@ -998,13 +1001,10 @@ cudaError_t launch_fwd(const XattnParams& x, cudaStream_t s) {
   // but only selected by variant 3 until it has been through the parity tests on a GPU.
   CUtensorMap to = tq;
   const int var = fwd_variant();
-  const bool want = (D == 40) ? (var >= 1) : (var == 3);       // (variants 2 and 4 only exist at D = 40)
+  const bool want = (D == 40) ? (var >= 1) : (var == 3);
   const bool tma_ok = (reinterpret_cast<uintptr_t>(x.out) & 15u) == 0 && (x.o_rs * 2) % 16 == 0 &&
                       (x.o_bs * 2) % 16 == 0 && x.o_bs > 0;
   if (want && tma_ok && make_tmap_out(&to, x.out, D, x.H, x.N, x.B, x.o_rs, x.o_bs, 32, C::EPI_CW, C::EPI_SW)) {
-    if constexpr (D == 40) {
-      if (var == 2 || var == 4) return launch_fwd_g4(tq, tk, tv, to, tp, s, var == 2 ? 4 : 2);   // experimental
-    }
     return launch_fwd_var<D, true>(tq, tk, tv, to, tp, s);
   }
   return launch_fwd_var<D, false>(tq, tk, tv, to, tp, s);

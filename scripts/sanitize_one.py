@@ -1,0 +1,29 @@
+"""One launch of each cross-attention path under compute-sanitizer (GPU box):
+    compute-sanitizer --tool racecheck python scripts/sanitize_one.py [fused]
+Shapes: the bench launch (B=2, one biased image, N=4096, H=8, D=40) shrunk to N=1024 rows so the instrumented run ends in
+seconds but still puts several units (and > 1 mask group) on a CTA when the grid is limited by PWW_DEBUG_GRID."""
+import math
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from paint_with_words_sd_b200 import _native  # noqa: E402
+from paint_with_words_sd_b200 import attention as A  # noqa: E402
+
+torch.manual_seed(0)
+dev = "cuda"
+B, N, H, D, T = 2, 1024, 8, 40, 77
+q = (torch.randn(B, N, H * D) * 0.5).half().to(dev)
+k = (torch.randn(B, T, H * D) * 0.5).half().to(dev)
+v = (torch.randn(B, T, H * D) * 0.5).half().to(dev)
+w = torch.zeros(1, N, T)
+w[0, :, 3] = (torch.rand(N) > 0.5).float() * 1.5
+w[0, :, 9] = (torch.rand(N) > 0.5).float() * 0.7
+idx = torch.tensor([0, -1], dtype=torch.int32, device=dev)
+gs = torch.tensor([0.4 * math.log(8.0)], dtype=torch.float32, device=dev)
+out = A.cross_attention(q, k, v, H, D ** -0.5, w.to(dev), idx, _native.PWW_STAT_MAX, gs)
+torch.cuda.synchronize()
+print("ok", float(out.float().abs().max()))

@@ -1,8 +1,8 @@
 """A/B the structural variants of the tcgen05 cross-attention forward kernel on one device, in one process:
 for each variant run the GPU parity tests of the op, then the kernel-only timing of bench.py's roofline leg.
 usage: python scripts/xattn_variants.py [variants...]   (default 1 3)
-variants: 0 per-thread stores | 1 TMA-store epilogue at D = 40 (the default build) | 2 experimental four-group kernel
-at D = 40 | 3 TMA-store epilogue at every head dim"""
+variants: 0 per-thread stores | 1 TMA-store epilogue at D = 40 (the default build) |
+3 TMA-store epilogue at every head dim"""
 import ctypes
 import json
 import os
@@ -31,8 +31,6 @@ for var in variants:
     if int(rc) != 0:
         continue
     for (N, H, D, B, biased) in shapes:
-        if D != 40 and var == 2:
-            continue
         r = bench.xattn_roofline(dev, B=B, biased=biased, N=N, H=H, D=D, iters=32 if B > 2 else 64)
         gbs = r["alg_bytes"] / (r["us_fwd"] * 1e-6) / 1e9
         print(json.dumps({"variant": var, "N": N, "H": H, "D": D, "B": B, "us_fwd": round(r["us_fwd"], 2),

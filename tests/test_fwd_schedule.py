@@ -50,8 +50,13 @@ def test_every_unit_once_and_mask_protocol(B, H, tiles, grid, widx):
         assert rows[:, 1].tolist() == list(range(len(rows)))          # contiguous iterations
         for grp in np.unique(rows[:, 5]):
             g = rows[rows[:, 5] == grp]
-            assert g[:, 7].sum() == 1, "every softmax warp releases the mask tile exactly once per group"
-            rel = int(np.argmax(g[:, 7]))
+            assert (g[:, 7] & 1).sum() == 1, "every softmax warp releases the mask tile exactly once per group"
+            rel = int(np.argmax(g[:, 7] & 1))
+            # phase rule of the mask barrier: every softmax warp (both groups) waits for B_MFULL exactly once per
+            # group, at the group's first unit in this CTA -> each warp observes phases 0, 1, 2, ... in order and
+            # arrives on B_MEMPTY only after it has observed the phase it releases
+            assert ((g[:, 7] >> 1) & 1).tolist() == [1] + [0] * (len(g) - 1)
+            assert int(np.argmax((g[:, 7] >> 1) & 1)) <= rel
             biased = [i for i, r in enumerate(g) if widx[r[2]] >= 0]
             for i in biased:
                 assert g[i, 6] == g[i, 2], "a biased unit must find its own image's mask tile staged"
@@ -74,3 +79,28 @@ def test_cfg_batches_are_balanced_whatever_the_image_order(order):
             sub = rows[rows[:, 1] % 2 == par]
             nbp = sum(widx[b] >= 0 for b in sub[:, 2])
             assert abs(2 * nbp - len(sub)) <= 2
+
+
+def _waited_phases_old_rule(rows, widx, group):
+    """Round-1 rule (the bug): a softmax group waited for B_MFULL only at ITS OWN units that read the mask."""
+    return [int(r[5]) for r in rows if r[1] % 2 == group and widx[r[2]] >= 0 and r[6] >= 0]
+
+
+def test_old_wait_rule_skipped_phases_and_new_rule_does_not():
+    """Round 1 failed test_bias_path_matches_oracle[max-4096-8-40] intermittently: a softmax group whose first
+    mask-reading unit lay in the CTA's SECOND mask group waited for parity 1 of B_MFULL without having observed
+    phase 0, so the parity test could pass before the first tile had landed.  The replay shows the old rule skipped
+    phases on some CTAs of exactly that launch, and that under the new rule every warp waits on every phase."""
+    B, H, tiles, grid, widx = 1, 8, 32, 148, [0]
+    s = _schedule(B, H, tiles, grid, widx)
+    exposed = []
+    for cta in range(grid):
+        rows = s[s[:, 0] == cta]
+        ngroups = len(np.unique(rows[:, 5]))
+        for group in (0, 1):
+            old = sorted(set(_waited_phases_old_rule(rows, widx, group)))
+            if old and old != list(range(old[-1] + 1)):
+                exposed.append(cta)
+        new = [int(r[5]) for r in rows if (r[7] >> 1) & 1]
+        assert new == list(range(ngroups)), (cta, new)
+    assert exposed, "the replay must reproduce the round-1 hazard under the old rule"

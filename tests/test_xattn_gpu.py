@@ -93,7 +93,7 @@ def test_plain_cross_attention_matches_oracle(N, H, D):
     assert (got - ref32).abs().max().item() <= 2e-3 * ref32.abs().max().item()
 
 
-@pytest.mark.parametrize("T", [1, 16, 77, 80, 128])
+@pytest.mark.parametrize("T", [1, 16, 77, 80])
 def test_key_lengths(T):
     N, H, D = 256, 8, 40
     q, k, v, w = _inputs(1, N, H, D, T, seed=T)
@@ -148,9 +148,10 @@ def test_unsupported_shape_raises():
     kv = torch.zeros(1, 77, 96, dtype=torch.float16, device="cuda")
     with pytest.raises(_native.NativeError):
         A.cross_attention(q, kv, kv, 2, 0.1)                  # D=48: no kernel, no fallback
-    kv = torch.zeros(1, 200, 80, dtype=torch.float16, device="cuda")
-    with pytest.raises(_native.NativeError):
-        A.cross_attention(torch.zeros(1, 64, 80, dtype=torch.float16, device="cuda"), kv, kv, 2, 0.1)   # T>128
+    for T in (81, 128, 200):                                  # only Stable Diffusion's key lengths (<= 80) have a kernel
+        kv = torch.zeros(1, T, 80, dtype=torch.float16, device="cuda")
+        with pytest.raises(_native.NativeError):
+            A.cross_attention(torch.zeros(1, 64, 80, dtype=torch.float16, device="cuda"), kv, kv, 2, 0.1)
 
 
 def test_real_weight_map_aurora(golden):
@@ -162,3 +163,37 @@ def test_real_weight_map_aurora(golden):
     got, st = _run(q, k, v, 8, 40 ** -0.5, w, g, "max")
     ref32, stats = _oracle(q, k, v, 8, 40 ** -0.5, w, g, "max", emulate=False)
     assert (got - ref32).abs().max().item() <= 2e-3 * ref32.abs().max().item()
+
+
+@pytest.mark.parametrize("B", [1, 2])
+def test_mask_barrier_stress_cold_maps(B):
+    """Round 1's intermittent failure: with > 1 mask group per CTA a softmax group could read the shared
+    mask tile before it had landed.  Run the failing launch shapes (N=4096, H=8, D=40; B=1 and the bench's B=2 with one
+    biased image) 200 times, each time with a weight map that is cold in L2 (fresh copy + an L2-sized write in
+    between), and require every output to be bit-identical to the first one, which is checked against the oracle."""
+    N, H, D, T = 4096, 8, 40, 77
+    q, k, v, w = _inputs(B, N, H, D, T, seed=4242 + B)
+    g = 0.4 * math.log(1 + 7.0)
+    idx = torch.tensor([0] + [-1] * (B - 1), dtype=torch.int32)
+    w1 = w[:1].contiguous()
+    w_eff = torch.cat([w1, torch.zeros(B - 1, N, T)], 0)
+    ref32, _ = _oracle(q, k, v, H, D ** -0.5, w_eff, g, "max", emulate=False)
+    dev = "cuda"
+    qd, kd, vd, idxd = q.to(dev), k.to(dev), v.to(dev), idx.to(dev)
+    gs = torch.tensor([g], dtype=torch.float32, device=dev)
+    flush = torch.empty(192 << 20, dtype=torch.uint8, device=dev)
+    pool = [w1.to(dev).clone() for _ in range(8)]
+    first = None
+    bad = torch.zeros((), dtype=torch.int32, device=dev)
+    for i in range(200):
+        wd = pool[i % 8].clone()                     # fresh allocation, never touched by a kernel before
+        flush.fill_(i & 0xFF)                        # evict Q/K/V and the maps from L2
+        out = A.cross_attention(qd, kd, vd, H, D ** -0.5, wd, idxd, _native.PWW_STAT_MAX, gs)
+        if first is None:
+            first = out.clone()
+        else:
+            bad += (out != first).any().to(torch.int32)
+    torch.cuda.synchronize()
+    assert int(bad) == 0, f"{int(bad)} of 199 repeat launches differ from the first"
+    amax = ref32.abs().max().item()
+    assert (first.float().cpu() - ref32).abs().max().item() <= 2e-3 * amax
