@@ -84,7 +84,7 @@ int pww_xattn_stats_f16(const void* q, const void* k,
  * `g_sigma` is a 1-element device array holding G(sigma) = coef*ln(1+sigma^p) for this step (a device
  * scalar so a captured CUDA graph can be replayed with a new sigma).  wmap/wmap_index/stats/g_sigma may
  * all be NULL: plain cross-attention (tensor context, paint_with_words.py:67-69,107-108).
- * Requires T <= 128.
+ * Requires T <= 80 (Stable Diffusion's 77-token context).
  */
 int pww_xattn_fwd_f16(const void* q, const void* k, const void* v, void* out,
                       int B, int H, int N, int T, int D,
@@ -93,6 +93,37 @@ int pww_xattn_fwd_f16(const void* q, const void* k, const void* v, void* out,
                       int64_t o_batch_stride, int64_t o_row_stride,
                       const float* wmap, int64_t wmap_batch_stride, const int32_t* wmap_index,
                       const float* stats, const float* g_sigma, float scale, void* stream);
+
+/*
+ * ONE-LAUNCH Paint-with-Words cross-attention: statistic + bias + softmax + P.V (paint_with_words.py:87-118 with the
+ * weight function of paint_with_words.py:402-405 inlined).  Replaces the pww_xattn_stats_f16 + pww_xattn_fwd_f16 pair:
+ * the per-image statistic is reduced inside the kernel (cooperative launch, deterministic fixed-order reduction of
+ * per-CTA partials) and the bias enters as two extra k-steps of the Q K^T tensor-core chain.
+ *
+ * The weight map is passed in PACKED form.  The reference's dense [N, T] fp32 map
+ * (paint_with_words.py:255-272) has one distinct non-zero column per painted region, so it is a column dictionary
+ *     W[n, t] = Mu[n, cidx[t]]       Mu [N, R] fp32, R <= 10 distinct columns; cidx[t] = -1 for an all-zero column
+ *   mpack : [Bw, N, 32] fp16, row n = [ hi(Mu[n,0..9]) | lo(Mu[n,0..9]) | hi(Mu[n,0..9]) | 0 0 ] with
+ *           hi(x) = fp16(x), lo(x) = fp16(x - hi(x));  64 bytes per pixel instead of 308
+ *           (element (w,n,c) at w*mpack_batch_stride + n*32 + c; 16-byte aligned)
+ *   cidx  : [Bw, 80] int8, dictionary column of token t (0..9) or -1 (also for t >= T)
+ * `paint_with_words_sd_b200.conditioning.pack_weight_map` builds both, bit-exactly reversible to the dense map.
+ * Maps with more than 10 distinct columns use the two-launch dense path above.
+ *
+ *   stats [B] out : the per-image statistic (fp16-rounded, as float; 0 for images without a map); may be NULL
+ *   workspace     : pww_xattn_fused_workspace_bytes() bytes, zero-filled ONCE after allocation (self-cleaning)
+ * mpack == NULL (or every wmap_index[b] < 0): plain cross-attention, workspace may be NULL.
+ * Requires T <= 80, B <= 32 per launch (larger batches are split internally), 16-byte aligned `out` strides.
+ */
+size_t pww_xattn_fused_workspace_bytes(void);
+int pww_xattn_fused_f16(const void* q, const void* k, const void* v, void* out,
+                        int B, int H, int N, int T, int D,
+                        int64_t q_batch_stride, int64_t q_row_stride,
+                        int64_t k_batch_stride, int64_t k_row_stride,
+                        int64_t o_batch_stride, int64_t o_row_stride,
+                        const void* mpack, int64_t mpack_batch_stride, int Bw, const int8_t* cidx,
+                        const int32_t* wmap_index, int stat, const float* g_sigma, float scale,
+                        float* stats, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Self-attention through the same patched function (context=None, paint_with_words.py:71-72):

@@ -17,6 +17,7 @@ PWW_STAT_MAX, PWW_STAT_STD = 0, 1
 EXPORTS = (
     "pww_version", "pww_status_str", "pww_last_cuda_error", "pww_device_supported",
     "pww_xattn_workspace_bytes", "pww_xattn_stats_f16", "pww_xattn_fwd_f16", "pww_attn_fwd_f16",
+    "pww_xattn_fused_workspace_bytes", "pww_xattn_fused_f16",
     "pww_groupnorm_workspace_bytes", "pww_groupnorm_nhwc_f16", "pww_geglu_f16", "pww_add_layernorm_f16",
 )
 
@@ -52,6 +53,11 @@ def lib() -> ctypes.CDLL:
     L.pww_xattn_fwd_f16.restype = c_i
     L.pww_xattn_fwd_f16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i, c_i, c_i, c_i, c_i, c_i64, c_i64, c_i64, c_i64,
                                     c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_f, c_vp]
+    L.pww_xattn_fused_workspace_bytes.restype = c_sz
+    L.pww_xattn_fused_workspace_bytes.argtypes = []
+    L.pww_xattn_fused_f16.restype = c_i
+    L.pww_xattn_fused_f16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i, c_i, c_i, c_i, c_i, c_i64, c_i64, c_i64, c_i64,
+                                      c_i64, c_i64, c_vp, c_i64, c_i, c_vp, c_vp, c_i, c_vp, c_f, c_vp, c_vp, c_sz, c_vp]
     L.pww_attn_fwd_f16.restype = c_i
     L.pww_attn_fwd_f16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i, c_i, c_i, c_i, c_i64, c_i64, c_i64, c_i64, c_f, c_vp]
     L.pww_groupnorm_workspace_bytes.restype = c_sz

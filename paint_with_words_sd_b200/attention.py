@@ -7,11 +7,12 @@ Same calling convention, context-dict schema and patch mechanism as the referenc
     context: None (self-attention) | Tensor[B,77,Dc] | dict with
         "CONTEXT_TENSOR", "CROSS_ATTENTION_WEIGHT_{N}" ([N,77] fp32 or int 0),
         "CROSS_ATTENTION_WEIGHT_ORIG" ([H,W,77] fp32 or int 0), "SIGMA", "WEIGHT_FUNCTION"
-        (optional, ours) "WMAP_INDEX", "G_SIGMA"
+        (optional, ours) "WMAP_INDEX", "G_SIGMA", "CROSS_ATTENTION_PACKED_{N}", "PWW_SCRATCH"
 
 Everything between the q/k/v projections and the output projection runs in libpww_b200.so through
-the C ABI (include/pww_b200.h): one stats launch (per-image max/std of QK^T over all heads) and one
-fused launch (bias + softmax + PV).  No score tensor, head permute or mask broadcast is materialised.
+the C ABI (include/pww_b200.h): ONE launch of `pww_xattn_fused_f16` (per-image max/std of QK^T over all heads,
+bias from the packed weight map, softmax, PV).  Maps with more than 10 distinct columns take the dense pair
+`pww_xattn_stats_f16` + `pww_xattn_fwd_f16`.  No score tensor, head permute or mask broadcast is materialised.
 There is no PyTorch/CPU fallback for the cross-attention path: unsupported shapes or weight functions
 raise.
 
@@ -31,7 +32,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _native
-from .conditioning import expand_orig_weight_map, weight_key
+from .conditioning import expand_orig_weight_map, pack_weight_map, packed_key, weight_key
 from .weight_function import g_of_sigma, probe_weight_function
 
 _ORIG_KEY = "CROSS_ATTENTION_WEIGHT_ORIG"
@@ -44,9 +45,14 @@ class _DeviceState:
         self.device = device
         self.g_sigma = torch.zeros(1, dtype=torch.float32, device=device)
         self._g_key = None
-        self.stats = torch.zeros(64, dtype=torch.float32, device=device)
-        self.workspace = torch.zeros(1 << 20, dtype=torch.uint8, device=device)
+        # Fixed-size scratch: captured CUDA graphs bake these addresses in, so they are never reallocated (ensure() raises
+        # instead of growing them).  8 MiB of dense-path workspace covers 127 images per call.
+        self.stats = torch.zeros(1024, dtype=torch.float32, device=device)
+        self.workspace = torch.zeros(8 << 20, dtype=torch.uint8, device=device)
+        # scratch of the one-launch kernel: fixed size, never reallocated (CUDA graphs bake its address in)
+        self.fused_ws = torch.zeros(_native.lib().pww_xattn_fused_workspace_bytes(), dtype=torch.uint8, device=device)
         self.index_cache: Dict[int, torch.Tensor] = {}
+        self.pack_cache: Dict[tuple, object] = {}
 
     def set_g(self, key, value: float) -> None:
         if key != self._g_key:
@@ -54,10 +60,24 @@ class _DeviceState:
             self._g_key = key
 
     def ensure(self, batch: int, ws_bytes: int) -> None:
-        if self.stats.numel() < batch:
-            self.stats = torch.zeros(batch, dtype=torch.float32, device=self.device)
-        if self.workspace.numel() < ws_bytes:
-            self.workspace = torch.zeros(ws_bytes, dtype=torch.uint8, device=self.device)
+        if self.stats.numel() < batch or self.workspace.numel() < ws_bytes:
+            raise _native.NativeError(f"batch of {batch} images exceeds the shim's fixed scratch; split the call or pass "
+                                      "your own stats_out/workspace")
+
+    def packed(self, wmap: torch.Tensor):
+        """Packed form of a dense device map, built once per (storage, version): the map is step-invariant, so the
+        torch.unique + split below runs at the first call only (outside any graph capture)."""
+        key = (wmap.data_ptr(), wmap._version, tuple(wmap.shape))
+        hit = self.pack_cache.get(key)
+        if hit is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise _native.NativeError("weight map must be packed before CUDA-graph capture (run one eager step first "
+                                          "or pass packed maps)")
+            if len(self.pack_cache) >= 64:
+                self.pack_cache.clear()
+            hit = pack_weight_map(wmap) or False
+            self.pack_cache[key] = hit
+        return hit or None
 
     def shared_index(self, batch: int) -> torch.Tensor:
         t = self.index_cache.get(batch)
@@ -104,12 +124,20 @@ def _rows(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+# "fused": one launch (statistic + bias + softmax + PV, packed maps); "dense": round-1 pair of launches on the dense fp32
+# map.  Maps that cannot be packed (> 10 distinct columns) always take the dense pair.  Test/bench knob.
+XATTN_IMPL = "fused"
+
+
 def cross_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: float,
                     wmap: Optional[torch.Tensor] = None, wmap_index: Optional[torch.Tensor] = None,
                     stat: int = _native.PWW_STAT_MAX, g_sigma: Optional[torch.Tensor] = None,
-                    return_stats: bool = False):
-    """Fused region for a key sequence of <=128 tokens.  q [B,N,C]; k,v [B,T,C]; wmap [Bw,N,T] fp32 or None.
-    `g_sigma` is a 1-element fp32 device tensor holding G(sigma)."""
+                    return_stats: bool = False, packed=None, stats_out: Optional[torch.Tensor] = None,
+                    workspace: Optional[torch.Tensor] = None):
+    """Fused region for a key sequence of <= 80 tokens.  q [B,N,C]; k,v [B,T,C]; wmap [Bw,N,T] fp32 or None;
+    `packed` = (mpack [Bw,N,32] fp16, cidx [Bw,80] int8) from `conditioning.pack_weight_map` (built from `wmap` and
+    cached when not given).  `g_sigma` is a 1-element fp32 device tensor holding G(sigma).  `stats_out` / `workspace`
+    let a caller that captures CUDA graphs own the scratch (defaults: per-device scratch of this module)."""
     L = _native.lib()
     q, k, v = _rows(q), _rows(k), _rows(v)
     B, N, C = q.shape
@@ -118,36 +146,69 @@ def cross_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: in
     if k.stride() != v.stride():
         v = v.contiguous()
         k = k.contiguous()
-    out = torch.empty((B, N, C), dtype=torch.float16, device=q.device)
     st = _state(q.device)
-    stream = torch.cuda.current_stream(q.device).cuda_stream
-    stats_ptr = g_ptr = w_ptr = idx_ptr = None
-    w_bs = 0
-    if wmap is not None:
-        if wmap.dtype != torch.float32 or not wmap.is_contiguous():
-            wmap = wmap.to(torch.float32).contiguous()
-        if wmap.dim() == 2:
-            wmap = wmap.unsqueeze(0)
-        if wmap.shape[1] != N or wmap.shape[2] != T:
-            raise ValueError(f"weight map shape {tuple(wmap.shape)} does not match N={N}, T={T}")
-        if wmap_index is None:
-            wmap_index = st.shared_index(B) if wmap.shape[0] == 1 else torch.arange(B, dtype=torch.int32, device=q.device)
-        ws_bytes = L.pww_xattn_workspace_bytes(B, heads, N, T, D)
-        st.ensure(B, ws_bytes)
-        rc = L.pww_xattn_stats_f16(q.data_ptr(), k.data_ptr(), B, heads, N, T, D, q.stride(0), q.stride(1),
-                                   k.stride(0), k.stride(1), stat, wmap_index.data_ptr(), st.stats.data_ptr(),
-                                   st.workspace.data_ptr(), st.workspace.numel(), stream)
-        _native.check(rc, "pww_xattn_stats_f16")
-        _native.launch_count += 1
-        stats_ptr, g_ptr = st.stats.data_ptr(), g_sigma.data_ptr()
-        w_ptr, idx_ptr, w_bs = wmap.data_ptr(), wmap_index.data_ptr(), wmap.stride(0)
-    rc = L.pww_xattn_fwd_f16(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, heads, N, T, D,
-                             q.stride(0), q.stride(1), k.stride(0), k.stride(1), out.stride(0), out.stride(1),
-                             w_ptr, w_bs, idx_ptr, stats_ptr, g_ptr, float(scale), stream)
-    _native.check(rc, "pww_xattn_fwd_f16")
-    _native.launch_count += 1
+    with torch.cuda.device(q.device):               # native launches go to q's device whatever the current one is
+        out = torch.empty((B, N, C), dtype=torch.float16, device=q.device)
+        stream = torch.cuda.current_stream(q.device).cuda_stream
+        biased = wmap is not None or packed is not None
+        if wmap is not None:
+            if wmap.dim() == 2:
+                wmap = wmap.unsqueeze(0)
+            if wmap.shape[1] != N or wmap.shape[2] != T:
+                raise ValueError(f"weight map shape {tuple(wmap.shape)} does not match N={N}, T={T}")
+        if biased and packed is None and XATTN_IMPL == "fused":
+            if wmap.dtype != torch.float32 or not wmap.is_contiguous():
+                wmap = wmap.to(torch.float32).contiguous()
+            packed = st.packed(wmap)
+        use_fused = XATTN_IMPL == "fused" and (not biased or packed is not None)
+        if biased and wmap_index is None:
+            bw = packed[0].shape[0] if packed is not None else wmap.shape[0]
+            wmap_index = st.shared_index(B) if bw == 1 else torch.arange(B, dtype=torch.int32, device=q.device)
+        stats = None
+        if use_fused:
+            mp_ptr = ci_ptr = idx_ptr = g_ptr = st_ptr = ws_ptr = None
+            mp_bs = bw = ws_bytes = 0
+            if biased:
+                mpack, cidx = packed
+                if mpack.shape[1] != N or mpack.dtype != torch.float16 or cidx.dtype != torch.int8:
+                    raise ValueError("packed weight map does not match this attention level")
+                st.ensure(B, 0)
+                stats = st.stats if stats_out is None else stats_out
+                ws = st.fused_ws if workspace is None else workspace
+                mp_ptr, ci_ptr, idx_ptr = mpack.data_ptr(), cidx.data_ptr(), wmap_index.data_ptr()
+                g_ptr, st_ptr, ws_ptr = g_sigma.data_ptr(), stats.data_ptr(), ws.data_ptr()
+                mp_bs, bw, ws_bytes = mpack.stride(0), mpack.shape[0], ws.numel()
+            rc = L.pww_xattn_fused_f16(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, heads, N, T, D,
+                                       q.stride(0), q.stride(1), k.stride(0), k.stride(1), out.stride(0), out.stride(1),
+                                       mp_ptr, mp_bs, bw, ci_ptr, idx_ptr, stat, g_ptr, float(scale), st_ptr, ws_ptr,
+                                       ws_bytes, stream)
+            _native.check(rc, "pww_xattn_fused_f16")
+            _native.launch_count += 1
+        else:
+            stats_ptr = g_ptr = w_ptr = idx_ptr = None
+            w_bs = 0
+            if biased:
+                if wmap is None:
+                    raise ValueError("the dense path needs the dense weight map")
+                if wmap.dtype != torch.float32 or not wmap.is_contiguous():
+                    wmap = wmap.to(torch.float32).contiguous()
+                ws_bytes = L.pww_xattn_workspace_bytes(B, heads, N, T, D)
+                st.ensure(B, ws_bytes)
+                stats = st.stats if stats_out is None else stats_out
+                rc = L.pww_xattn_stats_f16(q.data_ptr(), k.data_ptr(), B, heads, N, T, D, q.stride(0), q.stride(1),
+                                           k.stride(0), k.stride(1), stat, wmap_index.data_ptr(), stats.data_ptr(),
+                                           st.workspace.data_ptr(), st.workspace.numel(), stream)
+                _native.check(rc, "pww_xattn_stats_f16")
+                _native.launch_count += 1
+                stats_ptr, g_ptr = stats.data_ptr(), g_sigma.data_ptr()
+                w_ptr, idx_ptr, w_bs = wmap.data_ptr(), wmap_index.data_ptr(), wmap.stride(0)
+            rc = L.pww_xattn_fwd_f16(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, heads, N, T, D,
+                                     q.stride(0), q.stride(1), k.stride(0), k.stride(1), out.stride(0), out.stride(1),
+                                     w_ptr, w_bs, idx_ptr, stats_ptr, g_ptr, float(scale), stream)
+            _native.check(rc, "pww_xattn_fwd_f16")
+            _native.launch_count += 1
     if return_stats:
-        return out, (st.stats[:B].clone() if wmap is not None else None)
+        return out, (stats[:B].clone() if stats is not None else None)
     return out
 
 
@@ -165,10 +226,11 @@ def self_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int
         q, k, v = _rows(q), _rows(k), _rows(v)
         if not (q.stride() == k.stride() == v.stride()):
             q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
-        out = torch.empty((B, N, C), dtype=torch.float16, device=q.device)
-        rc = L.pww_attn_fwd_f16(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, heads, N, D,
-                                q.stride(0), q.stride(1), out.stride(0), out.stride(1), float(scale),
-                                torch.cuda.current_stream(q.device).cuda_stream)
+        with torch.cuda.device(q.device):
+            out = torch.empty((B, N, C), dtype=torch.float16, device=q.device)
+            rc = L.pww_attn_fwd_f16(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, heads, N, D,
+                                    q.stride(0), q.stride(1), out.stride(0), out.stride(1), float(scale),
+                                    torch.cuda.current_stream(q.device).cuda_stream)
         _native.check(rc, "pww_attn_fwd_f16")
         _native.launch_count += 1
         return out
@@ -232,7 +294,8 @@ def inj_forward(self, hidden_states, context=None, mask=None):
     if context is None:
         o = self_attention(q, k, v, self.heads, self.scale)
     else:
-        wmap = wmap_index = g_dev = None
+        wmap = wmap_index = g_dev = packed = None
+        scratch = (None, None)
         stat = _native.PWW_STAT_MAX
         if is_dict:
             f = context["WEIGHT_FUNCTION"]
@@ -247,10 +310,13 @@ def inj_forward(self, hidden_states, context=None, mask=None):
                     g_dev = st.g_sigma
                 wmap, stat = w, probed.stat
                 wmap_index = context.get("WMAP_INDEX")
+                packed = context.get(packed_key(q.shape[1]))          # (mpack, cidx) prepared by PwWSampler
+                scratch = context.get("PWW_SCRATCH", scratch)         # (stats, workspace) owned by the sampler
         if k.shape[0] != q.shape[0]:
             k = k.expand(q.shape[0], -1, -1)
             v = v.expand(q.shape[0], -1, -1)
-        o = cross_attention(q, k, v, self.heads, self.scale, wmap, wmap_index, stat, g_dev)
+        o = cross_attention(q, k, v, self.heads, self.scale, wmap, wmap_index, stat, g_dev, packed=packed,
+                            stats_out=scratch[0], workspace=scratch[1])
 
     with torch.autocast("cuda", dtype=torch.float16):
         o = self.to_out[0](o)

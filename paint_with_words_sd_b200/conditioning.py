@@ -115,6 +115,66 @@ def _tokens_img_attention_factors(img_context_seperated, tokenized_texts, ratio:
     return torch.stack(cols, dim=1), torch.stack(counts, dim=1)
 
 
+PACK_COLS = 32          # fp16 columns per pixel of the packed map (csrc/xattn_fused.cuh: kMW)
+PACK_CAPACITY = 10      # distinct non-zero columns a packed map can hold (kRC)
+PACK_TOKENS = 80        # padded token count of the column index (kTP)
+
+
+def pack_weight_map(w: torch.Tensor):
+    """Packed form of dense weight maps, the input of `pww_xattn_fused_f16`.
+
+    The reference's `[N, 77]` fp32 map (paint_with_words.py:255-272) is a sum of per-region columns: every token of a
+    region's label gets the SAME resized strength mask, so the map has only a handful of distinct non-zero columns
+    (one per region; one more per token that two regions share).  It is stored as a column dictionary
+
+        w[n, t] == Mu[n, cidx[t]]        Mu [N, R] fp32 (R <= 10), cidx[t] = -1 for an all-zero column
+
+    with Mu split into fp16 halves hi = fp16(Mu), lo = fp16(Mu - hi) so that hi + lo reproduces Mu to 2^-22:
+        mpack [Bw, N, 32] fp16 = [ hi(0..9) | lo(0..9) | hi(0..9) | 0 0 ],   cidx [Bw, 80] int8.
+    Works on CPU or CUDA tensors (torch ops only; the map builder is host-side set-up work, as in the reference).
+    Returns None when a map has more than PACK_CAPACITY distinct non-zero columns or values outside fp16 range --
+    such maps take the dense two-launch path."""
+    if w.dim() == 2:
+        w = w.unsqueeze(0)
+    bw, n, t = w.shape
+    if t > PACK_TOKENS:
+        return None
+    w = w.to(torch.float32)
+    mpack = torch.zeros((bw, n, PACK_COLS), dtype=torch.float16, device=w.device)
+    cidx = torch.full((bw, PACK_TOKENS), -1, dtype=torch.int8, device=w.device)
+    for i in range(bw):
+        cols = torch.nonzero((w[i] != 0).any(dim=0)).flatten()
+        if cols.numel() == 0:
+            continue
+        uniq, inv = torch.unique(w[i][:, cols].t().contiguous(), dim=0, return_inverse=True)   # rows = distinct columns
+        r = uniq.shape[0]
+        if r > PACK_CAPACITY or not torch.isfinite(uniq).all() or float(uniq.abs().max()) > 6.0e4:
+            return None
+        hi = uniq.to(torch.float16)
+        lo = (uniq - hi.to(torch.float32)).to(torch.float16)
+        mpack[i, :, 0:r] = hi.t()
+        mpack[i, :, PACK_CAPACITY:PACK_CAPACITY + r] = lo.t()
+        mpack[i, :, 2 * PACK_CAPACITY:2 * PACK_CAPACITY + r] = hi.t()
+        cidx[i, cols] = inv.to(torch.int8)
+    return mpack, cidx
+
+
+def unpack_weight_map(mpack: torch.Tensor, cidx: torch.Tensor, tokens: int = 77) -> torch.Tensor:
+    """Inverse of `pack_weight_map` (tests / documentation): dense [Bw, N, tokens] fp32 with hi + lo per entry."""
+    bw, n, _ = mpack.shape
+    mu = mpack[..., :PACK_CAPACITY].to(torch.float32) + mpack[..., PACK_CAPACITY:2 * PACK_CAPACITY].to(torch.float32)
+    out = torch.zeros((bw, n, tokens), dtype=torch.float32, device=mpack.device)
+    for i in range(bw):
+        idx = cidx[i, :tokens].to(torch.int64)
+        sel = idx >= 0
+        out[i][:, sel] = mu[i][:, idx[sel]]
+    return out
+
+
+def packed_key(n: int) -> str:
+    return f"CROSS_ATTENTION_PACKED_{n}"
+
+
 def _extract_seed_and_sigma_from_context(color_context: dict, ignore_seed: int = -1):
     """paint_with_words.py:279-297: "label,strength[,seed[,blur_sigma]]".  Mutates `color_context`."""
     extra_seeds: Dict[int, int] = {}

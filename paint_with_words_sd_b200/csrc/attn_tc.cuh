@@ -343,11 +343,11 @@ cudaError_t launch(const void* q, const void* k, const void* v, void* out, int B
     return cudaErrorInvalidValue;
   Params p;
   p.out = (__half*)out; p.B = B; p.H = H; p.N = N; p.o_bs = o_bs; p.o_rs = o_rs; p.scale = scale;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[tc::kMaxDevices] = {false};
+  if (!attr_set[tc::cur_device()]) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[tc::cur_device()] = true;
   }
   const int qtiles = (N + 128 * C::NQ - 1) / (128 * C::NQ);
   attn_fwd_tc_kernel<D><<<B * H * qtiles, kThreads, C::SMEM, s>>>(tq, tk, tv, p);

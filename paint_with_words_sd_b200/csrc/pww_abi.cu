@@ -4,6 +4,7 @@
 
 #include "pww_common.cuh"
 #include "xattn_tc.cuh"
+#include "xattn_fused.cuh"
 #include "attn_tc.cuh"
 #include "unet_ops.cuh"
 #include <stdlib.h>
@@ -158,6 +159,65 @@ int pww_xattn_fwd_f16(const void* q, const void* k, const void* v, void* out, in
   }
 }
 
+size_t pww_xattn_fused_workspace_bytes(void) { return pww::fx::fused_workspace_bytes(); }
+
+int pww_xattn_fused_f16(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int T, int D,
+                        int64_t q_batch_stride, int64_t q_row_stride, int64_t k_batch_stride, int64_t k_row_stride,
+                        int64_t o_batch_stride, int64_t o_row_stride, const void* mpack, int64_t mpack_batch_stride,
+                        int Bw, const int8_t* cidx, const int32_t* wmap_index, int stat, const float* g_sigma,
+                        float scale, float* stats, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common(q, k, B, H, N, T, D, q_batch_stride, q_row_stride, k_batch_stride, k_row_stride);
+  if (rc) return rc;
+  if (!v || !out || !aligned16(v) || !aligned16(out)) return PWW_ERR_BAD_ARG;
+  if ((o_batch_stride | o_row_stride) & 7 || o_row_stride < (int64_t)H * D || o_batch_stride <= 0) return PWW_ERR_BAD_ARG;
+  if (mpack) {
+    if (!cidx || !g_sigma || !workspace || Bw <= 0 || !aligned16(mpack)) return PWW_ERR_BAD_ARG;
+    if ((mpack_batch_stride & 7) || mpack_batch_stride < (int64_t)N * pww::fx::kMW) return PWW_ERR_BAD_ARG;
+    if (stat != PWW_STAT_MAX && stat != PWW_STAT_STD) return PWW_ERR_BAD_ARG;
+    if (workspace_bytes < pww_xattn_fused_workspace_bytes()) return PWW_ERR_WORKSPACE;
+  }
+  pww::XattnParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = (const __half*)q; p.k = (const __half*)k; p.v = (const __half*)v; p.out = (__half*)out;
+  p.B = B; p.H = H; p.N = N; p.T = T; p.D = D;
+  p.q_bs = q_batch_stride; p.q_rs = q_row_stride; p.k_bs = k_batch_stride; p.k_rs = k_row_stride;
+  p.o_bs = o_batch_stride; p.o_rs = o_row_stride;
+  p.g_sigma = g_sigma; p.scale = scale; p.stat = stat;
+  p.counters = (unsigned int*)workspace;
+  p.partials = workspace ? (pww::StatPartial*)((char*)workspace + 256) : nullptr;
+  cudaStream_t s = (cudaStream_t)stream;
+  // image b is biased iff it has a packed map: with mpack == NULL every index is -1 (the kernel reads wmap_index)
+  for (int b0 = 0; b0 < B; b0 += pww::fx::kMaxBatch) {            // <= 32 images per launch
+    pww::XattnParams c = p;
+    c.B = (B - b0) < pww::fx::kMaxBatch ? (B - b0) : pww::fx::kMaxBatch;
+    c.q = p.q + (int64_t)b0 * p.q_bs;
+    c.k = p.k + (int64_t)b0 * p.k_bs;
+    c.v = p.v + (int64_t)b0 * p.k_bs;
+    c.out = p.out + (int64_t)b0 * p.o_bs;
+    c.stats_out = stats ? stats + b0 : nullptr;
+    const void* mp = mpack;
+    const int8_t* ci = cidx;
+    if (mpack && wmap_index) {
+      c.wmap_index = wmap_index + b0;
+    } else if (mpack) {                                            // identity mapping: image b uses map b
+      c.wmap_index = nullptr;
+      mp = (const __half*)mpack + (int64_t)b0 * mpack_batch_stride;
+      ci = cidx + (int64_t)b0 * pww::fx::kTP;
+    }
+    c.wmap = mpack ? (const float*)mp : nullptr;                   // non-null marks "maps present" for the kernel
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (D) {
+      case 40: e = pww::fx::launch_fused<40>(c, mp, mpack_batch_stride, Bw, ci, s); break;
+      case 64: e = pww::fx::launch_fused<64>(c, mp, mpack_batch_stride, Bw, ci, s); break;
+      case 80: e = pww::fx::launch_fused<80>(c, mp, mpack_batch_stride, Bw, ci, s); break;
+      case 160: e = pww::fx::launch_fused<160>(c, mp, mpack_batch_stride, Bw, ci, s); break;
+    }
+    if (e == cudaErrorInvalidConfiguration) return PWW_ERR_UNSUPPORTED;
+    if (e != cudaSuccess) return cuda_fail(e);
+  }
+  return PWW_OK;
+}
+
 size_t pww_groupnorm_workspace_bytes(int B, int HW, int G) {
   if (B <= 0 || HW <= 0 || G <= 0) return 0;
   return align_up((size_t)B * sizeof(unsigned int), 256) + align_up((size_t)B * G * 2 * sizeof(float), 256) +
@@ -262,6 +322,22 @@ int pww_debug_set_variant(int variant) {
 int pww_debug_fwd_schedule(int B, int H, int tiles, int grid, const int* wmap_index, int* out) {
   if (!wmap_index || !out) return PWW_ERR_BAD_ARG;
   return pww::tc::fwd_schedule_host(B, H, tiles, grid, wmap_index, out);
+}
+
+// Test infrastructure (not declared in the public header): cap the persistent grid of the fused kernel (0 = all SMs) so
+// small shapes exercise long job lists; replay the fused kernel's job lists on the host (10 int32 per job, see
+// fused_schedule_host); does CTA `cta` contribute a partial to image b's statistic?
+int pww_debug_set_fused_grid(int grid) {
+  pww::fx::debug_grid() = grid < 0 ? 0 : grid;
+  return PWW_OK;
+}
+int pww_debug_fused_schedule(int B, int H, int tiles, int grid, const int* wmap_index, int* out, int max_jobs) {
+  if (!wmap_index || !out) return PWW_ERR_BAD_ARG;
+  return pww::fx::fused_schedule_host(B, H, tiles, grid, wmap_index, out, max_jobs);
+}
+int pww_debug_fused_cta_has_image(int cta, int grid, int B, int H, int tiles, const int* wmap_index, int b) {
+  if (!wmap_index) return PWW_ERR_BAD_ARG;
+  return pww::fx::fused_cta_has_image_host(cta, grid, B, H, tiles, wmap_index, b);
 }
 
 int pww_attn_fwd_f16(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int D,

@@ -891,14 +891,18 @@ inline bool make_tmap(CUtensorMap* m, const void* base, int D, int H, int L, int
   return r == CUDA_SUCCESS;
 }
 
+// Per-device host state: the current device decides (the Python shim makes the tensors' device current).
+constexpr int kMaxDevices = 64;
+inline int cur_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
 inline int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
+  static int n[kMaxDevices] = {0};
+  const int dev = cur_device();
+  if (!n[dev]) cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+  return n[dev];
 }
 
 inline int stats_grid(int units) { return units < num_sms() ? units : num_sms(); }
@@ -937,9 +941,9 @@ inline int fwd_schedule_host(int B, int H, int tiles, int grid, const int* wmap_
   return row;
 }
 
-// Forward-kernel epilogue: 0 = per-thread global stores everywhere, 1 = TMA-store epilogue at D = 40 (default),
-// 3 = TMA-store epilogue at every head dim; pww_debug_set_variant overrides it for A/B timing.
-constexpr int kDefaultFwdVariant = 1;
+// Forward-kernel epilogue: 0 = per-thread global stores everywhere, 1 = TMA-store epilogue at D = 40 only,
+// 3 = TMA-store epilogue at every head dim (default); pww_debug_set_variant overrides it for A/B timing.
+constexpr int kDefaultFwdVariant = 3;   // parity-green and faster at D = 64 / 80 / 160 on hardware (profiles/r02_call1_*)
 inline int& fwd_variant() {
   static int v = kDefaultFwdVariant;
   return v;
@@ -965,13 +969,13 @@ cudaError_t launch_fwd_var(const CUtensorMap& tq, const CUtensorMap& tk, const C
   using C = Cfg<D>;
   constexpr uint32_t smem = EPI_TMA ? C::SMEM_EPI : C::SMEM;
   static_assert(smem <= 232448 - 8192, "shared memory budget (dynamic + static tables)");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {false};       // cudaFuncSetAttribute is per device
+  if (!attr_set[cur_device()]) {
     cudaError_t e = cudaFuncSetAttribute(xattn_fwd_tc_kernel<D, 77, EPI_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(xattn_fwd_tc_kernel<D, 0, EPI_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[cur_device()] = true;
   }
   const int grid = tp.units < num_sms() ? tp.units : num_sms();
   if (tp.x.T == 77)
@@ -1024,13 +1028,13 @@ cudaError_t launch_stats(const XattnParams& x, cudaStream_t s) {
   tp.units = x.B * tp.tiles * x.H;
   tp.k_batched = x.k_bs > 0 ? 1 : 0;
   tp.timeline = debug_timeline();
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {false};
+  if (!attr_set[cur_device()]) {
     cudaError_t e = cudaFuncSetAttribute(xattn_stats_tc_kernel<D, 77>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::S_SMEM);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(xattn_stats_tc_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::S_SMEM);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[cur_device()] = true;
   }
   if (x.T == 77)
     xattn_stats_tc_kernel<D, 77><<<stats_grid(tp.units), kThreads, C::S_SMEM, s>>>(tq, tk, tp);

@@ -15,11 +15,18 @@ _WS: Dict[torch.device, torch.Tensor] = {}
 
 
 def _workspace(device, nbytes: int) -> torch.Tensor:
+    """GroupNorm scratch.  A larger request gets a NEW buffer; the old one stays alive in `_WS_KEEP` because captured
+    CUDA graphs may still hold its address (a graph only ever sees the buffer that was current when it was captured)."""
     w = _WS.get(device)
     if w is None or w.numel() < nbytes:
-        w = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)   # counters must start at zero
+        if w is not None:
+            _WS_KEEP.append(w)
+        w = torch.zeros(max(nbytes, 4 << 20), dtype=torch.uint8, device=device)   # counters must start at zero
         _WS[device] = w
     return w
+
+
+_WS_KEEP: list = []
 
 
 def is_fast(x: torch.Tensor) -> bool:
@@ -41,10 +48,11 @@ def group_norm_nhwc(x: torch.Tensor, gn: torch.nn.GroupNorm, add: Optional[torch
         if add.dtype != torch.float16 or add.stride(-1) != 1 or (add.stride(0) % 8) or (add.data_ptr() % 16):
             add = add.to(torch.float16).contiguous()
         add_bs = add.stride(0)
-    rc = L.pww_groupnorm_nhwc_f16(x.data_ptr(), None if add is None else add.data_ptr(), add_bs, gn.weight.data_ptr(),
-                                  gn.bias.data_ptr(), y.data_ptr(), B, H * W, C, gn.num_groups, float(gn.eps),
-                                  1 if silu else 0, ws.data_ptr(), ws.numel(),
-                                  torch.cuda.current_stream(x.device).cuda_stream)
+    with torch.cuda.device(x.device):
+        rc = L.pww_groupnorm_nhwc_f16(x.data_ptr(), None if add is None else add.data_ptr(), add_bs, gn.weight.data_ptr(),
+                                      gn.bias.data_ptr(), y.data_ptr(), B, H * W, C, gn.num_groups, float(gn.eps),
+                                      1 if silu else 0, ws.data_ptr(), ws.numel(),
+                                      torch.cuda.current_stream(x.device).cuda_stream)
     _native.check(rc, "pww_groupnorm_nhwc_f16")
     _native.launch_count += 2
     return y
@@ -57,7 +65,8 @@ def geglu(h: torch.Tensor) -> torch.Tensor:
     I = h.shape[-1] // 2
     M = h.numel() // h.shape[-1]
     out = torch.empty(h.shape[:-1] + (I,), dtype=h.dtype, device=h.device)
-    rc = _native.lib().pww_geglu_f16(h.data_ptr(), out.data_ptr(), M, I, torch.cuda.current_stream(h.device).cuda_stream)
+    with torch.cuda.device(h.device):
+        rc = _native.lib().pww_geglu_f16(h.data_ptr(), out.data_ptr(), M, I, torch.cuda.current_stream(h.device).cuda_stream)
     _native.check(rc, "pww_geglu_f16")
     _native.launch_count += 1
     return out
@@ -73,9 +82,11 @@ def add_layer_norm(x: torch.Tensor, res: Optional[torch.Tensor], ln: torch.nn.La
     M = x.numel() // C
     y = torch.empty_like(x)
     s = torch.empty_like(x) if (res is not None and want_sum) else None
-    rc = _native.lib().pww_add_layernorm_f16(x.data_ptr(), None if res is None else res.data_ptr(), ln.weight.data_ptr(),
-                                             ln.bias.data_ptr(), None if s is None else s.data_ptr(), y.data_ptr(), M, C,
-                                             float(ln.eps), torch.cuda.current_stream(x.device).cuda_stream)
+    with torch.cuda.device(x.device):
+        rc = _native.lib().pww_add_layernorm_f16(x.data_ptr(), None if res is None else res.data_ptr(),
+                                                 ln.weight.data_ptr(), ln.bias.data_ptr(),
+                                                 None if s is None else s.data_ptr(), y.data_ptr(), M, C,
+                                                 float(ln.eps), torch.cuda.current_stream(x.device).cuda_stream)
     _native.check(rc, "pww_add_layernorm_f16")
     _native.launch_count += 1
     return (x if res is None else s), y

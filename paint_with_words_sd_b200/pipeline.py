@@ -21,7 +21,7 @@ import torch.nn.functional as F
 from PIL import Image
 
 from . import attention as _attention
-from .conditioning import _encode_text_color_inputs, _get_binary_mask
+from .conditioning import _encode_text_color_inputs, _get_binary_mask, pack_weight_map, packed_key
 from .scheduler import LMSDiscreteScheduler
 from .synthetic import IdentityVAE, RandomTextEncoder, SimpleWordTokenizer
 from .unet import UNet2DConditionModel, UNetConfig, build_unet
@@ -82,9 +82,14 @@ def pww_load_tools(device: str = "cuda:0", scheduler_type=LMSDiscreteScheduler,
     return vae, unet, text_encoder, tokenizer, scheduler
 
 
+def _module_dtype(module, default=torch.float32):
+    p = next(iter(module.parameters()), None) if hasattr(module, "parameters") else None
+    return p.dtype if p is not None else default
+
+
 def _pil_from_latents(vae, latents):
-    """paint_with_words.py:48-57."""
-    image = vae.decode(1 / 0.18215 * latents.clone()).sample
+    """paint_with_words.py:48-57.  (The reference runs under torch.autocast; here the VAE gets its own dtype.)"""
+    image = vae.decode((1 / 0.18215 * latents.clone()).to(_module_dtype(vae, latents.dtype))).sample
     image = (image / 2 + 0.5).clamp(0, 1).detach().cpu().permute(0, 2, 3, 1).float().numpy()
     return [Image.fromarray(a) for a in (image * 255).round().astype("uint8")]
 
@@ -137,6 +142,8 @@ class PwWSampler:
         self._kv_graph = None
         self.native_launches_per_step = None
         self._probed = probe_weight_function(weight_function, 1.0)
+        up = next(iter(unet.parameters()), None)
+        self._unet_dtype = up.dtype if up is not None else torch.float32
         self._ctx = self._merge_contexts(cond_ctxs, uncond_ctxs)
         dev = self.device
         # Per-step scalars (sigma, 1/sqrt(sigma^2+1), t, 4 LMS coefficients, G(sigma)) are tabulated
@@ -176,13 +183,24 @@ class PwWSampler:
                 ctx[key] = vals[0] if m == 1 else 0   # ORIG fallback is a single-image path
                 continue
             if all(isinstance(v, torch.Tensor) for v in vals):
-                ctx[key] = torch.stack([v.to(self.device, torch.float32) for v in vals], 0).contiguous()
+                dense = torch.stack([v.detach().to("cpu", torch.float32) for v in vals], 0).contiguous()
+                ctx[key] = dense.to(self.device)
+                packed = pack_weight_map(dense)      # host-side set-up, like the map builder itself
+                if packed is not None:
+                    n = int(key.rsplit("_", 1)[1])
+                    ctx[packed_key(n)] = (packed[0].to(self.device), packed[1].to(self.device))
             else:
                 ctx[key] = 0
         ctx["WMAP_INDEX"] = torch.tensor(list(range(m)) + [-1] * m, dtype=torch.int32, device=self.device)
         ctx["WEIGHT_FUNCTION"] = self.weight_function
         ctx["SIGMA"] = None
         ctx["KV_CACHE"] = {}       # to_k/to_v of the text context are step-invariant: computed at the first step
+        # scratch of the attention launches, owned by this sampler: its captured graphs never see a buffer that another
+        # sampler or a later, larger call replaced
+        from . import _native
+        ctx["PWW_SCRATCH"] = (torch.zeros(max(64, 2 * m), dtype=torch.float32, device=self.device),
+                              torch.zeros(_native.lib().pww_xattn_fused_workspace_bytes(), dtype=torch.uint8,
+                                          device=self.device))
         return ctx
 
     # -- one step, expressed only with device tensors / device scalars --------------------------
@@ -191,7 +209,7 @@ class PwWSampler:
         x = self.latents * self._params[1]
         if self.extra_input is not None:
             x = torch.cat([x, self.extra_input], dim=1)
-        x2 = torch.cat([x, x], 0)
+        x2 = torch.cat([x, x], 0).to(self._unet_dtype)      # the reference runs under autocast: feed the UNet its own dtype
         eps = self.unet(x2, self._params[2:3], encoder_hidden_states=self._ctx).sample.float()
         eps_c, eps_u = eps[:m], eps[m:]
         noise_pred = eps_u + self.guidance_scale * (eps_c - eps_u)
@@ -211,8 +229,12 @@ class PwWSampler:
         Copying new values INTO them (same addresses) is valid between graph replays."""
         d = {"latents": self.latents, "CONTEXT_TENSOR": self._ctx["CONTEXT_TENSOR"]}
         for k, v in self._ctx.items():
-            if k.startswith("CROSS_ATTENTION_WEIGHT_") and isinstance(v, torch.Tensor) and v.is_cuda:
-                d[k] = v
+            if k.startswith("CROSS_ATTENTION_PACKED_"):
+                d[k + "_M"], d[k + "_C"] = v                       # packed map + token column index
+            elif k.startswith("CROSS_ATTENTION_WEIGHT_") and isinstance(v, torch.Tensor) and v.is_cuda:
+                n = k.rsplit("_", 1)[1]
+                if n.isdigit() and packed_key(int(n)) not in self._ctx:
+                    d[k] = v                                       # dense map (only when it could not be packed)
         return d
 
     def stage_from_host(self, pinned: Dict[str, torch.Tensor]) -> int:
@@ -326,7 +348,7 @@ def paint_with_words(
         t_start = max(num_inference_steps - init_timestep, 0)
         timesteps = scheduler.timesteps[t_start:]
         image = preprocess(init_image).to(device=device)
-        init_latents = 0.18215 * vae.encode(image).latent_dist.sample()
+        init_latents = 0.18215 * vae.encode(image.to(_module_dtype(vae, image.dtype))).latent_dist.sample().float()
         noise = torch.randn(init_latents.shape).to(device)
         latents = scheduler.add_noise(init_latents, noise, timesteps[:1])
 
@@ -406,12 +428,12 @@ def paint_with_words_inpaint(
 
     generator = torch.manual_seed(seed)
     image = preprocess(init_image).to(device=device)
-    init_latents = 0.18215 * vae.encode(image).latent_dist.sample()
+    init_latents = 0.18215 * vae.encode(image.to(_module_dtype(vae, image.dtype))).latent_dist.sample().float()
     noise = torch.randn(init_latents.shape, generator=generator).to(device)
     latents = scheduler.add_noise(init_latents, noise, timesteps[:1])
 
     mask = F.interpolate(mask, size=(height // 8, width // 8)).to(device=device, dtype=latents.dtype)
-    masked_image_latents = 0.18215 * vae.encode(masked_image.to(device=device, dtype=latents.dtype)).latent_dist.sample()
+    masked_image_latents = 0.18215 * vae.encode(masked_image.to(device=device, dtype=_module_dtype(vae, latents.dtype))).latent_dist.sample().float()
     mask = F.interpolate(mask, size=latents.shape[-2:], mode="nearest")
     masked_image_latents = F.interpolate(masked_image_latents, size=latents.shape[-2:], mode="nearest")
     total = latents.shape[1] + mask.shape[1] + masked_image_latents.shape[1]

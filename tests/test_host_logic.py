@@ -202,3 +202,43 @@ def test_product_attention_refuses_cpu():
     m = attention_modules(unet)[0]
     with pytest.raises(RuntimeError):
         P.inj_forward(m, torch.randn(1, 16, 32))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# packed weight maps: the column dictionary the one-launch kernel consumes
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["aurora_512", "cat_dog_512", "aurora_256", "cat_dog_256"])
+@pytest.mark.parametrize("ratio", [8, 16, 32, 64])
+def test_pack_weight_map_reproduces_the_reference_maps(golden, name, ratio):
+    """pack -> unpack gives back the map the REFERENCE built (tests/golden/mask_builder.npz) to hi+lo fp16 precision:
+    relative 2^-21 (two fp16 mantissas) or the fp16 subnormal step 2^-25 absolute, whichever is larger; the zero
+    pattern and the column sharing are exact."""
+    from paint_with_words_sd_b200.conditioning import PACK_CAPACITY, pack_weight_map, unpack_weight_map
+    w = torch.from_numpy(golden["mask_builder"][f"{name}_w{ratio}"])
+    packed = pack_weight_map(w)
+    assert packed is not None
+    mpack, cidx = packed
+    assert mpack.shape == (1, w.shape[0], 32) and mpack.dtype == torch.float16 and cidx.shape == (1, 80)
+    assert int(cidx.max()) < PACK_CAPACITY and (cidx[0, 77:] == -1).all()
+    rec = unpack_weight_map(mpack, cidx)[0]
+    assert torch.equal(rec == 0, w == 0)
+    assert ((rec - w).abs() <= torch.clamp(2.0 ** -21 * w.abs(), min=2.0 ** -25)).all()
+    # tokens of one label share a dictionary entry: as many entries as distinct non-zero columns
+    nz = [tuple(w[:, t].tolist()) for t in range(77) if (w[:, t] != 0).any()]
+    assert len(set(nz)) == int(cidx.max()) + 1
+    assert (mpack[0, :, :10] == mpack[0, :, 20:30]).all() and (mpack[0, :, 30:] == 0).all()
+
+
+def test_pack_weight_map_limits():
+    from paint_with_words_sd_b200.conditioning import pack_weight_map
+    n = 64
+    w = torch.zeros(2, n, 77)
+    mp, ci = pack_weight_map(w)                                   # all-zero maps pack to nothing
+    assert (mp == 0).all() and (ci == -1).all()
+    g = torch.Generator().manual_seed(0)
+    w[1, :, :11] = torch.rand(n, 11, generator=g)                 # 11 distinct columns: over capacity
+    assert pack_weight_map(w) is None
+    w[1, :, 10] = w[1, :, 9]                                      # ... 10 distinct: fits
+    assert pack_weight_map(w) is not None
+    w[0, 0, 0] = 1.0e5                                            # outside fp16 range
+    assert pack_weight_map(w) is None

@@ -54,26 +54,36 @@ def _oracle(q, k, v, H, scale, w, g, stat, emulate):
     return torch.cat(outs, 0), stats
 
 
-def _run(q, k, v, H, scale, w, g, stat, idx=None):
+IMPLS = ["fused", "dense"]      # one-launch kernel on packed maps | round-1 pair of launches on the dense fp32 map
+
+
+def _run(q, k, v, H, scale, w, g, stat, idx=None, impl="fused"):
     dev = "cuda"
     gs = torch.tensor([g], dtype=torch.float32, device=dev)
-    out, st = A.cross_attention(q.to(dev), k.to(dev), v.to(dev), H, scale,
-                                None if w is None else w.to(dev), None if idx is None else idx.to(dev),
-                                _native.PWW_STAT_MAX if stat == "max" else _native.PWW_STAT_STD, gs, return_stats=True)
-    torch.cuda.synchronize()
+    old = A.XATTN_IMPL
+    A.XATTN_IMPL = impl
+    try:
+        out, st = A.cross_attention(q.to(dev), k.to(dev), v.to(dev), H, scale,
+                                    None if w is None else w.to(dev), None if idx is None else idx.to(dev),
+                                    _native.PWW_STAT_MAX if stat == "max" else _native.PWW_STAT_STD, gs,
+                                    return_stats=True)
+        torch.cuda.synchronize()
+    finally:
+        A.XATTN_IMPL = old
     return out.float().cpu(), (None if st is None else st.cpu())
 
 
+@pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("N,H,D", SD15_512 + SD15_256 + SD21_768 + RAGGED)
 @pytest.mark.parametrize("stat", ["max", "std"])
-def test_bias_path_matches_oracle(N, H, D, stat):
+def test_bias_path_matches_oracle(N, H, D, stat, impl):
     if stat == "std" and N * H > 40000:
         pytest.skip("std covered at the smaller sizes; max covers the large ones")
     T, B = 77, 1
     q, k, v, w = _inputs(B, N, H, D, T, seed=N * 131 + D)
     scale = D ** -0.5
     g = 0.4 * math.log(1 + 7.0) if stat == "max" else 0.5 * math.log(1 + 7.0 ** 2)
-    got, st = _run(q, k, v, H, scale, w, g, stat)
+    got, st = _run(q, k, v, H, scale, w, g, stat, impl=impl)
     ref16, st16 = _oracle(q, k, v, H, scale, w, g, stat, emulate=True)
     ref32, _ = _oracle(q, k, v, H, scale, w, g, stat, emulate=False)
     if N * H * T > 1:
@@ -83,34 +93,37 @@ def test_bias_path_matches_oracle(N, H, D, stat):
     assert (got - ref32).abs().max().item() <= 2e-3 * amax
 
 
-@pytest.mark.parametrize("N,H,D", [(4096, 8, 40), (64, 8, 160), (576, 20, 64)])
-def test_plain_cross_attention_matches_oracle(N, H, D):
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("N,H,D", [(4096, 8, 40), (64, 8, 160), (576, 20, 64), (1024, 8, 80)])
+def test_plain_cross_attention_matches_oracle(N, H, D, impl):
     """Tensor context / uncond dict: no bias (paint_with_words.py:107-110)."""
     q, k, v, _ = _inputs(2, N, H, D, 77, seed=7)
-    got, st = _run(q, k, v, H, D ** -0.5, None, 0.0, "max")
+    got, st = _run(q, k, v, H, D ** -0.5, None, 0.0, "max", impl=impl)
     ref32, _ = _oracle(q, k, v, H, D ** -0.5, None, 0.0, "max", emulate=False)
     assert st is None
     assert (got - ref32).abs().max().item() <= 2e-3 * ref32.abs().max().item()
 
 
-@pytest.mark.parametrize("T", [1, 16, 77, 80])
-def test_key_lengths(T):
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("T", [1, 16, 41, 77, 80])
+def test_key_lengths(T, impl):
     N, H, D = 256, 8, 40
     q, k, v, w = _inputs(1, N, H, D, T, seed=T)
     g = 0.7
-    got, st = _run(q, k, v, H, D ** -0.5, w, g, "max")
+    got, st = _run(q, k, v, H, D ** -0.5, w, g, "max", impl=impl)
     ref32, st32 = _oracle(q, k, v, H, D ** -0.5, w, g, "max", emulate=False)
     assert (got - ref32).abs().max().item() <= 2e-3 * ref32.abs().max().item()
 
 
-def test_batched_cfg_semantics_per_image_stats():
+@pytest.mark.parametrize("impl", IMPLS)
+def test_batched_cfg_semantics_per_image_stats(impl):
     """[cond0, uncond, cond1] in one call: per-image statistic, index -1 = no bias, maps picked by index."""
     N, H, D, T = 1024, 8, 80, 77
     q, k, v, w = _inputs(3, N, H, D, T, seed=99)
     q[2] *= 3.0                                     # make the images' maxima very different
     idx = torch.tensor([1, -1, 0], dtype=torch.int32)
     g = 0.4 * math.log(1 + 3.0)
-    got, st = _run(q, k, v, H, D ** -0.5, w[:2].contiguous(), g, "max", idx)
+    got, st = _run(q, k, v, H, D ** -0.5, w[:2].contiguous(), g, "max", idx, impl=impl)
     w_eff = torch.stack([w[1], torch.zeros_like(w[0]), w[0]])
     ref, stats = _oracle(q, k, v, H, D ** -0.5, w_eff, g, "max", emulate=False)
     ref_plain, _ = _oracle(q[1:2], k[1:2], v[1:2], H, D ** -0.5, None, 0.0, "max", emulate=False)
@@ -120,7 +133,7 @@ def test_batched_cfg_semantics_per_image_stats():
     assert (got[1] - ref_plain[0]).abs().max().item() <= 2e-3 * amax
     assert float(st[1]) == 0.0 and abs(float(st[2]) - stats[2]) <= 2e-3 * abs(stats[2])
     # batching does not change an image's result (sharding invariance): bit-identical
-    solo, _ = _run(q[2:3], k[2:3], v[2:3], H, D ** -0.5, w[0:1].contiguous(), g, "max")
+    solo, _ = _run(q[2:3], k[2:3], v[2:3], H, D ** -0.5, w[0:1].contiguous(), g, "max", impl=impl)
     assert torch.equal(solo[0], got[2])
 
 
@@ -135,11 +148,12 @@ def test_strided_views_no_copy_semantics():
     assert (out.float().cpu() - ref32).abs().max().item() <= 2e-3 * ref32.abs().max().item()
 
 
-def test_stats_workspace_is_self_cleaning():
+@pytest.mark.parametrize("impl", IMPLS)
+def test_stats_workspace_is_self_cleaning(impl):
     N, H, D = 1024, 8, 80
     q, k, v, w = _inputs(2, N, H, D, 77, seed=3)
-    a, sa = _run(q, k, v, H, D ** -0.5, w, 0.5, "std")
-    b, sb = _run(q, k, v, H, D ** -0.5, w, 0.5, "std")
+    a, sa = _run(q, k, v, H, D ** -0.5, w, 0.5, "std", impl=impl)
+    b, sb = _run(q, k, v, H, D ** -0.5, w, 0.5, "std", impl=impl)
     assert torch.equal(a, b) and torch.equal(sa, sb)          # deterministic, counters reset
 
 
@@ -154,19 +168,21 @@ def test_unsupported_shape_raises():
             A.cross_attention(torch.zeros(1, 64, 80, dtype=torch.float16, device="cuda"), kv, kv, 2, 0.1)
 
 
-def test_real_weight_map_aurora(golden):
+@pytest.mark.parametrize("impl", IMPLS)
+def test_real_weight_map_aurora(golden, impl):
     """aurora_1 map at N=4096 (config 2 of BASELINE.json), default-style weight function."""
     mb = golden["mask_builder"]
     w = torch.from_numpy(mb["aurora_512_w8"])[None]
     q, k, v, _ = _inputs(1, 4096, 8, 40, 77, seed=2026)
     g = 0.4 * math.log(1 + 14.6146)
-    got, st = _run(q, k, v, 8, 40 ** -0.5, w, g, "max")
+    got, st = _run(q, k, v, 8, 40 ** -0.5, w, g, "max", impl=impl)
     ref32, stats = _oracle(q, k, v, 8, 40 ** -0.5, w, g, "max", emulate=False)
     assert (got - ref32).abs().max().item() <= 2e-3 * ref32.abs().max().item()
 
 
+@pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("B", [1, 2])
-def test_mask_barrier_stress_cold_maps(B):
+def test_mask_barrier_stress_cold_maps(B, impl):
     """Round 1's intermittent failure: with > 1 mask group per CTA a softmax group could read the shared
     mask tile before it had landed.  Run the failing launch shapes (N=4096, H=8, D=40; B=1 and the bench's B=2 with one
     biased image) 200 times, each time with a weight map that is cold in L2 (fresh copy + an L2-sized write in
@@ -185,15 +201,113 @@ def test_mask_barrier_stress_cold_maps(B):
     pool = [w1.to(dev).clone() for _ in range(8)]
     first = None
     bad = torch.zeros((), dtype=torch.int32, device=dev)
+    A.XATTN_IMPL = impl
+    packed_pool = None
+    if impl == "fused":
+        from paint_with_words_sd_b200.conditioning import pack_weight_map
+        packed_pool = [pack_weight_map(p_) for p_ in pool]
     for i in range(200):
         wd = pool[i % 8].clone()                     # fresh allocation, never touched by a kernel before
+        pk = None
+        if packed_pool is not None:
+            pk = (packed_pool[i % 8][0].clone(), packed_pool[i % 8][1].clone())
         flush.fill_(i & 0xFF)                        # evict Q/K/V and the maps from L2
-        out = A.cross_attention(qd, kd, vd, H, D ** -0.5, wd, idxd, _native.PWW_STAT_MAX, gs)
+        out = A.cross_attention(qd, kd, vd, H, D ** -0.5, wd, idxd, _native.PWW_STAT_MAX, gs, packed=pk)
         if first is None:
             first = out.clone()
         else:
             bad += (out != first).any().to(torch.int32)
     torch.cuda.synchronize()
+    A.XATTN_IMPL = "fused"
     assert int(bad) == 0, f"{int(bad)} of 199 repeat launches differ from the first"
     amax = ref32.abs().max().item()
     assert (first.float().cpu() - ref32).abs().max().item() <= 2e-3 * amax
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# one-launch kernel specifics
+# ------------------------------------------------------------------------------------------------------------------
+def _set_fused_grid(n):
+    import ctypes
+    L = _native.lib()
+    L.pww_debug_set_fused_grid.argtypes = [ctypes.c_int]
+    assert L.pww_debug_set_fused_grid(n) == 0
+
+
+@pytest.mark.parametrize("N,H,D,B,grid", [(1024, 8, 40, 4, 8), (1024, 8, 40, 2, 3), (2304, 10, 64, 4, 16),
+                                          (1024, 8, 80, 6, 12), (256, 8, 160, 8, 5), (333, 3, 40, 5, 4)])
+@pytest.mark.parametrize("stat", ["max", "std"])
+def test_fused_long_job_lists(N, H, D, B, grid, stat):
+    """A capped persistent grid puts 10-40 jobs on every CTA: ring stages, score slots, output accumulators, the
+    B-operand tile of the bias and the exchange buffers are all reused many times, and CTAs span several images."""
+    T = 77
+    q, k, v, w = _inputs(B, N, H, D, T, seed=B * 1000 + N + D)
+    nb = (B + 1) // 2
+    idx = torch.tensor([(i // 2 if i % 2 == 0 else -1) for i in range(B)], dtype=torch.int32)   # cond/uncond interleaved
+    g = 0.4 * math.log(1 + 5.0)
+    w_eff = torch.stack([w[i // 2] if i % 2 == 0 else torch.zeros(N, T) for i in range(B)])
+    _set_fused_grid(grid)
+    try:
+        got, st = _run(q, k, v, H, D ** -0.5, w[:nb].contiguous(), g, stat, idx)
+    finally:
+        _set_fused_grid(0)
+    ref32, stats = _oracle(q, k, v, H, D ** -0.5, w_eff, g, stat, emulate=False)
+    amax = ref32.abs().max().item()
+    assert (got - ref32).abs().max().item() <= 2e-3 * amax
+    for b in range(B):
+        if idx[b] < 0:
+            assert float(st[b]) == 0.0
+        else:
+            assert abs(float(st[b]) - stats[b]) <= 2e-3 * abs(stats[b]) + 1e-6
+    # the full grid gives bit-identical results: the statistic does not depend on how units are split over CTAs
+    full, st_full = _run(q, k, v, H, D ** -0.5, w[:nb].contiguous(), g, stat, idx)
+    if stat == "max":
+        assert torch.equal(full, got) and torch.equal(st_full, st)
+
+
+def test_fused_all_biased_and_all_unbiased_batches():
+    """Batches without a partner image of the other kind (solo groups of the unit order)."""
+    N, H, D, T = 1024, 8, 40, 77
+    q, k, v, w = _inputs(3, N, H, D, T, seed=77)
+    g = 0.9
+    got, st = _run(q, k, v, H, D ** -0.5, w, g, "max")                       # all biased, identity map index
+    ref32, stats = _oracle(q, k, v, H, D ** -0.5, w, g, "max", emulate=False)
+    assert (got - ref32).abs().max().item() <= 2e-3 * ref32.abs().max().item()
+    idx = torch.tensor([2, -1, -1], dtype=torch.int32)                       # one biased, two unbiased
+    got, st = _run(q, k, v, H, D ** -0.5, w, g, "max", idx)
+    w_eff = torch.stack([w[2], torch.zeros(N, T), torch.zeros(N, T)])
+    ref32, _ = _oracle(q, k, v, H, D ** -0.5, w_eff, g, "max", emulate=False)
+    assert (got - ref32).abs().max().item() <= 2e-3 * ref32.abs().max().item()
+
+
+def test_fused_more_than_ten_columns_takes_the_dense_pair():
+    """A map with 30 distinct columns cannot be packed: the shim must route it to the dense two-launch path."""
+    N, H, D, T = 256, 8, 40, 77
+    q, k, v, _ = _inputs(1, N, H, D, T, seed=11)
+    gen = torch.Generator().manual_seed(5)
+    w = torch.zeros(1, N, T)
+    w[0, :, :30] = torch.rand(N, 30, generator=gen)
+    from paint_with_words_sd_b200.conditioning import pack_weight_map
+    assert pack_weight_map(w) is None
+    before = _native.launch_count
+    got, st = _run(q, k, v, H, D ** -0.5, w, 0.6, "max")
+    assert _native.launch_count - before == 2
+    ref32, _ = _oracle(q, k, v, H, D ** -0.5, w, 0.6, "max", emulate=False)
+    assert (got - ref32).abs().max().item() <= 2e-3 * ref32.abs().max().item()
+
+
+def test_fused_is_one_launch_and_large_bias_precision():
+    """One native launch per call; and the hi/lo split of map and coefficient keeps a LARGE bias exact: strength 8 with
+    g = 3 puts logits at several hundred, where a plain fp16 product (2^-11 relative) would be off by ~0.1."""
+    N, H, D, T = 1024, 8, 40, 77
+    q, k, v, _ = _inputs(1, N, H, D, T, seed=21)
+    gen = torch.Generator().manual_seed(9)
+    w = torch.zeros(1, N, T)
+    base = torch.rand(N, 3, generator=gen) * 8.0
+    w[0, :, 4] = base[:, 0]; w[0, :, 5] = base[:, 0]; w[0, :, 20] = base[:, 1]; w[0, :, 33] = base[:, 2]
+    w[0, :, 20] += base[:, 0]                                   # a token shared by two regions: its own dictionary entry
+    before = _native.launch_count
+    got, st = _run(q, k, v, H, D ** -0.5, w, 3.0, "max")
+    assert _native.launch_count - before == 1
+    ref32, _ = _oracle(q, k, v, H, D ** -0.5, w, 3.0, "max", emulate=False)
+    assert (got - ref32).abs().max().item() <= 2e-3 * ref32.abs().max().item()
