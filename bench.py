@@ -15,9 +15,11 @@ One JSON line on stdout (rank 0):
   value      steps/s over all ranks, inputs resident in HBM, CUDA-graph replay, CUDA-event time, max over ranks
   e2e        the same steps driven from HOST buffers: every step H2D-copies latents, text context and the four
              weight maps from pinned memory, runs the step, and D2H-reads the new latents (sync per step)
-  roofline   the dominant kernel of the path -- pww_xattn_fwd_f16 at N=4096 (C=320, 8 heads) -- timed live with CUDA
-             events as a graph of back-to-back launches over rotating buffers larger than L2, at the batch this
-             workload launches it with (cond+uncond); `batched` repeats it with 16 images per launch
+  roofline   the dominant kernel of the path -- pww_xattn_fused_f16 (ONE launch: statistic + bias + softmax + PV) at
+             N=4096 (C=320, 8 heads) -- timed live with CUDA events as a graph of back-to-back launches over rotating
+             buffers larger than L2, at the batch this workload launches it with (cond+uncond); `batched` repeats it
+             with 16 images per launch; `dense_pair` times the round-1 two-launch path on the same inputs
+  reference_gpu_eager   comparison only: the reference's loop and inj_forward op sequence as eager fp16 PyTorch on this GPU
   cpu_baseline  the oracle port of the reference loop on this box's host cores (rank 0, N=1 only), bounded sample
 --impl reference: only that CPU loop (the reference is pure Python/torch; its CPU path is what is timed).
 """
@@ -54,19 +56,90 @@ def weight_function(w, sigma, qk):          # runner.py:104
     return 0.4 * w * math.log(1 + sigma) * qk.max()
 
 
-def workload_config(n_gpus: int) -> dict:
-    return {"workload": "configs[1]: aurora_1 colour map, SD1.5-shape UNet 512x512, 30-step LMS, CFG 7.5, fp16, "
-                        "weight_function 0.4*w*log(1+sigma)*qk.max()",
-            "images_per_gpu": 1, "unet_batch": 2, "global_images": n_gpus, "latent": [4, SIZE // 8, SIZE // 8],
-            "tokens": 77, "parallelism": f"image-sharded x{n_gpus}, weights replicated (1 broadcast), no per-step collective",
-            "l2_policy": "inputs larger than L2: each step streams the 1.7 GB of fp16 UNet weights (L2 is 126 MB)"}
+def workload_config(n_gpus: int, cfg_id: int = 2, images_per_gpu: int = 1) -> dict:
+    cfg = CONFIGS[cfg_id]
+    size = cfg["size"]
+    total = cfg["total_images"] or n_gpus
+    return {"workload": f"{cfg['tag']}: {cfg['what']}; weight_function {cfg['coef']}*w*log(1+sigma)*qk.max()",
+            "images_per_gpu": images_per_gpu, "unet_batch": 2 * images_per_gpu, "global_images": total,
+            "latent": [4, size // 8, size // 8], "tokens": 77,
+            "parallelism": f"image-sharded x{n_gpus}, weights replicated (1 broadcast), no per-step collective",
+            "l2_policy": "inputs larger than L2: each step streams the fp16 UNet weights (1.7 GB; L2 is 126 MB)"}
+
+
+# BASELINE.json configs (1-based, BASELINE.md section 4 numbering).  The driver runs the default (2 = configs[1], the
+# configuration the metric is quoted on); `--config N` measures the others with the same machinery
+# (scripts/bench_configs.sh fills BASELINE.md's table from them).  "weak": one image per GPU; "strong": a fixed set of
+# images sharded over the GPUs (image i -> rank i mod G).
+CONFIGS = {
+    1: dict(tag="configs[0]", what="runner.py cat/dog colour map, SD1.5-shape UNet 256x256, 10-step LMS, CFG 7.5 "
+                                  "(the reference runs this one on the CPU)",
+            unet="sd15", size=256, sched_steps=10, maps=["cat_dog"], coef=0.4, text_dim=768, total_images=None),
+    2: dict(tag="configs[1]", what="aurora_1 colour map, SD1.5-shape UNet 512x512, 30-step LMS, CFG 7.5, fp16",
+            unet="sd15", size=512, sched_steps=30, maps=["aurora"], coef=0.4, text_dim=768, total_images=None),
+    3: dict(tag="configs[2]", what="4 colour maps x 2 seeds = 8 images (16 forward items), SD1.5-shape 512x512, 30 steps, "
+                                  "image-sharded",
+            unet="sd15", size=512, sched_steps=30, maps=["aurora", "cat_dog", "aurora/flip", "cat_dog/flip"], coef=0.4,
+            text_dim=768, total_images=8),
+    4: dict(tag="configs[3]", what="paint_with_words_inpaint: SD1.5-inpainting-shape UNet (9 input channels) 512x512, "
+                                  "moon_mask, 50 steps, weight 0.15",
+            unet="sd15_inpaint", size=512, sched_steps=50, maps=["aurora"], coef=0.15, text_dim=768, total_images=None,
+            inpaint=True),
+    5: dict(tag="configs[4]", what="SD2.1-shape UNet (d=64, ctx 1024, linear proj) 768x768, 50 steps, 5-region colour "
+                                  "context with regional seeding, 8 images (16 forward items), image-sharded",
+            unet="sd21", size=768, sched_steps=50, maps=["aurora"], coef=0.4, text_dim=1024, total_images=8,
+            region_seeds=True),
+}
+
+
+def make_weight_function(coef: float):
+    def wf(w, sigma, qk):                   # runner.py:94,104 (0.4) / runner_inpaint.py:72,87 (0.15)
+        return coef * w * math.log(1 + sigma) * qk.max()
+    return wf
+
+
+def unet_config(name: str):
+    return {"sd15": UNetConfig.sd15, "sd15_inpaint": UNetConfig.sd15_inpaint, "sd21": UNetConfig.sd21}[name]()
+
+
+def build_images(cfg: dict, device, image_ids, tok, enc, sch):
+    """Conditioning + initial latents of the images this rank owns.  Returns (conds, unconds, latents [m,4,h,w],
+    extra_input or None)."""
+    from PIL import Image as _Image
+    from paint_with_words_sd_b200.pipeline import initial_latents
+    size = cfg["size"]
+    conds, unconds, lats, extras = [], [], [], []
+    for i in image_ids:
+        spec = cfg["maps"][i % len(cfg["maps"])]
+        name, flip = (spec.split("/") + [""])[:2]
+        seed = i // len(cfg["maps"]) if cfg["total_images"] else i
+        img = color_map_image(name, size)
+        if flip:
+            img = img.transpose(_Image.FLIP_LEFT_RIGHT)
+        ctx = dict(SETTINGS[name]["ctx"])
+        if cfg.get("region_seeds"):                      # runner.py:61-72 style: ",seed" on one region
+            key = list(ctx.keys())[-1]
+            ctx[key] = ctx[key] + ",2077"
+        extra_seeds, separated, cond, uncond = _encode_text_color_inputs(enc, tok, device, img, ctx,
+                                                                         SETTINGS[name]["prompt"], "")
+        lat = initial_latents((1, 4, size // 8, size // 8), seed, extra_seeds, separated) * sch.init_noise_sigma
+        conds.append(cond); unconds.append(uncond); lats.append(lat)
+        if cfg.get("inpaint"):                           # paint_with_words_inpaint.py:230-250: cat[latents, mask, masked latents]
+            import torch.nn.functional as F_
+            from tests.fixtures import moon_mask_image
+            m = torch.from_numpy(np.array(moon_mask_image(size)).astype(np.float32) / 255.0)[None, None]
+            m = F_.interpolate((m > 0.5).float(), size=(size // 8, size // 8), mode="nearest")
+            masked = torch.randn(1, 4, size // 8, size // 8, generator=torch.manual_seed(1000 + seed)) * 0.18215 * (1 - m)
+            extras.append(torch.cat([m, masked], 1))
+    extra = torch.cat(extras, 0).to(device) if extras else None
+    return conds, unconds, torch.cat(lats, 0).to(device), extra
 
 
 def ncu_traffic(key: str):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
-    (profiles/r01_xattn_traffic.json, produced from gpurun_out/r01_xattn_B*.ncu-rep); None if absent."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the
+    one-launch kernel (profiles/r02_xattn_traffic.json, written by scripts/ncu_summary.py); None if absent."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_xattn_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_xattn_traffic.json")) as f:
             return float(json.load(f)[key]["traffic_bytes"])
     except Exception:
         return None
@@ -135,6 +208,11 @@ class ClockSampler:
 def cpu_reference(max_timed_steps: int, warmup: int, budget_s: float):
     """Timed oracle loop on the host cores: same UNet weights (seed 0, fp32), same conditioning, same schedule."""
     from oracle import loop as oracle_loop
+    # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses every host core it can, whatever launched it
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     torch.manual_seed(0)
     unet = build_unet(UNetConfig.sd15(), seed=0, dtype=torch.float32, device="cpu")
     oracle_loop.patch_with_oracle(unet)
@@ -190,39 +268,73 @@ def run_reference_arm(args, rank: int):
 # ------------------------------------------------------------------------------------------------
 # kernel roofline (live, CUDA events)
 # ------------------------------------------------------------------------------------------------
-def xattn_roofline(device, B: int, biased: int, N=4096, H=8, D=40, T=77, target_mb=192, iters=64, reps=5):
-    """Average duration of pww_xattn_stats_f16 and pww_xattn_fwd_f16 over a CUDA graph of back-to-back launches that
-    cycle through enough distinct buffer sets to exceed L2 (so Q/W/O really come from / go to HBM)."""
+def region_weight_map(N: int, T: int = 77, regions: int = 5, seed: int = 0) -> torch.Tensor:
+    """A dense [N, T] fp32 weight map with the structure the reference's builder produces (paint_with_words.py:247-276):
+    `regions` painted regions, each a contiguous band of pixels with its own strength and soft edge, each attached to
+    1-3 prompt tokens.  Used where no golden map of that resolution exists (kernel timing only)."""
+    g = torch.Generator().manual_seed(seed)
+    w = torch.zeros(N, T)
+    edges = torch.linspace(0, N, regions + 1).long().tolist()
+    tok = 5
+    for r in range(regions):
+        col = torch.zeros(N)
+        lo, hi = edges[r], edges[r + 1]
+        col[lo:hi] = float(torch.rand(1, generator=g) * 1.8 + 0.2)
+        if hi - lo > 8:
+            col[lo:lo + 4] *= torch.linspace(0.2, 0.8, 4)      # bilinear-resize style soft edge
+        ntok = 1 + r % 3
+        for t in range(tok, tok + ntok):
+            w[:, t] = col
+        tok += ntok + 1
+    return w
+
+
+def golden_weight_map(N: int):
+    """The real aurora_1 map at this resolution when the golden fixtures hold it (SD1.5 512x512 levels), else None."""
+    key = {4096: "aurora_512_w8", 1024: "aurora_512_w16", 256: "aurora_512_w32", 64: "aurora_512_w64"}.get(N)
+    if key is None:
+        return None
+    return torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "mask_builder.npz"))[key])
+
+
+def xattn_roofline(device, B: int, biased: int, N=4096, H=8, D=40, T=77, target_mb=192, iters=64, reps=5,
+                   dense_pair: bool = False):
+    """Average duration of ONE pww_xattn_fused_f16 launch over a CUDA graph of back-to-back launches that cycle through
+    enough distinct buffer sets to exceed L2 (so Q / packed maps / O really come from / go to HBM).  Maps: the golden
+    aurora_1 map of that resolution (or a region-structured synthetic one), packed by conditioning.pack_weight_map.
+    dense_pair=True additionally times pww_xattn_stats_f16 + pww_xattn_fwd_f16 on the dense fp32 form of the same maps."""
     from paint_with_words_sd_b200 import _native
+    from paint_with_words_sd_b200.conditioning import pack_weight_map
     L = _native.lib()
     C = H * D
-    per_set = B * N * C * 2 * 2 + biased * N * T * 4
+    per_set = B * N * C * 2 * 2 + biased * N * 64
     nsets = max(2, int(math.ceil(target_mb * 1e6 / per_set)))
     g = torch.Generator(device="cpu").manual_seed(0)
     qs = [(torch.randn(B, N, C, generator=g) * 0.5).half().to(device) for _ in range(nsets)]
     outs = [torch.empty(B, N, C, dtype=torch.float16, device=device) for _ in range(nsets)]
     k = (torch.randn(B, T, C, generator=g) * 0.5).half().to(device)
     v = (torch.randn(B, T, C, generator=g) * 0.5).half().to(device)
-    ws = [(torch.rand(biased, N, T, generator=g) > 0.8).float().to(device) for _ in range(nsets)]
+    base = golden_weight_map(N)
+    if base is None:
+        base = region_weight_map(N, T)
+    dense = torch.stack([base] * max(1, biased), 0).contiguous()
+    mp0, ci0 = pack_weight_map(dense)
+    mps = [mp0.to(device).clone() for _ in range(nsets)]
+    ci = ci0.to(device)
     idx = torch.tensor(list(range(biased)) + [-1] * (B - biased), dtype=torch.int32, device=device)
     stats = torch.zeros(B, dtype=torch.float32, device=device)
     gs = torch.full((1,), 0.4 * math.log(1 + 7.0), dtype=torch.float32, device=device)
-    ws_bytes = L.pww_xattn_workspace_bytes(B, H, N, T, D)
-    work = torch.zeros(ws_bytes, dtype=torch.uint8, device=device)
+    fws = torch.zeros(L.pww_xattn_fused_workspace_bytes(), dtype=torch.uint8, device=device)
     scale = D ** -0.5
 
-    def launch_stats(i, stream):
-        q = qs[i % nsets]
-        rc = L.pww_xattn_stats_f16(q.data_ptr(), k.data_ptr(), B, H, N, T, D, q.stride(0), q.stride(1), k.stride(0),
-                                   k.stride(1), 0, idx.data_ptr(), stats.data_ptr(), work.data_ptr(), ws_bytes, stream)
-        _native.check(rc, "stats")
-
-    def launch_fwd(i, stream):
-        q, o, w = qs[i % nsets], outs[i % nsets], ws[i % nsets]
-        rc = L.pww_xattn_fwd_f16(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, H, N, T, D, q.stride(0),
-                                 q.stride(1), k.stride(0), k.stride(1), o.stride(0), o.stride(1), w.data_ptr(),
-                                 w.stride(0), idx.data_ptr(), stats.data_ptr(), gs.data_ptr(), scale, stream)
-        _native.check(rc, "fwd")
+    def launch_fused(i, stream):
+        q, o, mp = qs[i % nsets], outs[i % nsets], mps[i % nsets]
+        rc = L.pww_xattn_fused_f16(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, H, N, T, D, q.stride(0),
+                                   q.stride(1), k.stride(0), k.stride(1), o.stride(0), o.stride(1),
+                                   mp.data_ptr() if biased else None, mp.stride(0), mp.shape[0],
+                                   ci.data_ptr() if biased else None, idx.data_ptr() if biased else None, 0,
+                                   gs.data_ptr(), scale, stats.data_ptr(), fws.data_ptr(), fws.numel(), stream)
+        _native.check(rc, "fused")
 
     def timed(fn):
         s = torch.cuda.Stream(device=device)
@@ -245,12 +357,30 @@ def xattn_roofline(device, B: int, biased: int, N=4096, H=8, D=40, T=77, target_
             best.append(e0.elapsed_time(e1) * 1e3 / iters)     # us per launch
         return float(np.median(best))
 
-    launch_stats(0, torch.cuda.current_stream(device).cuda_stream)
-    torch.cuda.synchronize(device)
-    t_stats = timed(launch_stats)
-    t_fwd = timed(launch_fwd)
-    alg_bytes = B * (2 * N * C * 2 + 2 * T * C * 2) + biased * N * T * 4
-    return {"us_stats": t_stats, "us_fwd": t_fwd, "alg_bytes": alg_bytes, "sets": nsets, "iters": iters}
+    t_fused = timed(launch_fused)
+    qkvo = B * (2 * N * C * 2 + 2 * T * C * 2)
+    res = {"us_op": t_fused, "alg_bytes": qkvo + biased * (N * 64 + 80), "alg_bytes_dense_map": qkvo + biased * N * T * 4,
+           "sets": nsets, "iters": iters}
+    if dense_pair and biased:
+        ws = [dense.to(device).clone() for _ in range(min(nsets, 8))]
+        ws_bytes = L.pww_xattn_workspace_bytes(B, H, N, T, D)
+        work = torch.zeros(ws_bytes, dtype=torch.uint8, device=device)
+
+        def launch_stats(i, stream):
+            q = qs[i % nsets]
+            rc = L.pww_xattn_stats_f16(q.data_ptr(), k.data_ptr(), B, H, N, T, D, q.stride(0), q.stride(1), k.stride(0),
+                                       k.stride(1), 0, idx.data_ptr(), stats.data_ptr(), work.data_ptr(), ws_bytes, stream)
+            _native.check(rc, "stats")
+
+        def launch_fwd(i, stream):
+            q, o, w = qs[i % nsets], outs[i % nsets], ws[i % len(ws)]
+            rc = L.pww_xattn_fwd_f16(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, H, N, T, D, q.stride(0),
+                                     q.stride(1), k.stride(0), k.stride(1), o.stride(0), o.stride(1), w.data_ptr(),
+                                     w.stride(0), idx.data_ptr(), stats.data_ptr(), gs.data_ptr(), scale, stream)
+            _native.check(rc, "fwd")
+
+        res["us_dense_stats"], res["us_dense_fwd"] = timed(launch_stats), timed(launch_fwd)
+    return res
 
 
 def eager_torch_xattn_us(device, N=4096, H=8, D=40, T=77, iters=20, dtype=torch.float16):
@@ -296,6 +426,68 @@ def eager_torch_xattn_us(device, N=4096, H=8, D=40, T=77, iters=20, dtype=torch.
     return e0.elapsed_time(e1) * 1e3 / iters
 
 
+def reference_gpu_eager(device, steps: int, warmup: int):
+    """Comparison only ("the real bar"; SURVEY 8d last line): the REFERENCE's control flow and op
+    sequence as eager fp16 PyTorch on this GPU -- two batch-1 UNet forwards per step (paint_with_words.py:483-499),
+    inj_forward's op sequence under torch.autocast (paint_with_words.py:60-125: three projections, heads->batch copies,
+    QK^T, weight function with qk.max(), bias add, softmax, PV, batch->heads copy, to_out), the host-side sigma lookup
+    with its `.nonzero().item()` sync (paint_with_words.py:473) and the stock PyTorch UNet route (no fused ops, no
+    CUDA graph, no K/V caching).  Same UNet weights (seed 0), same conditioning, same schedule as the b200 arm.
+    Returns steps/s (CUDA events).  Patches CrossAttention.__call__ class-wide; the caller re-patches afterwards."""
+    from oracle import loop as oracle_loop
+    from paint_with_words_sd_b200 import fused_ops
+    from paint_with_words_sd_b200.unet import CrossAttention
+
+    @torch.autocast("cuda")
+    def eager_inj_forward(self, hidden_states, context=None, mask=None):
+        as_dict = isinstance(context, dict)
+        ctx = hidden_states if context is None else (context["CONTEXT_TENSOR"] if as_dict else context)
+        q, k, v = (self.reshape_heads_to_batch_dim(t) for t in (self.to_q(hidden_states), self.to_k(ctx), self.to_v(ctx)))
+        scores = torch.matmul(q, k.transpose(-1, -2))
+        bias = 0.0
+        if as_dict:
+            bias = context["WEIGHT_FUNCTION"](context[f"CROSS_ATTENTION_WEIGHT_{scores.shape[-2]}"], context["SIGMA"], scores)
+        probs = ((scores + bias) * self.scale).softmax(dim=-1)
+        out = self.reshape_batch_dim_to_heads(torch.matmul(probs, v))
+        return self.to_out[1](self.to_out[0](out))
+
+    unet = build_unet(UNetConfig.sd15(), seed=0, dtype=torch.float16, device=device)
+    tok, enc = SimpleWordTokenizer(), RandomTextEncoder(768).to(device)
+    st = SETTINGS["aurora"]
+    _, _, cond, uncond = _encode_text_color_inputs(enc, tok, device, color_map_image("aurora", SIZE), dict(st["ctx"]),
+                                                   st["prompt"], "")
+    cond.pop("CROSS_ATTENTION_WEIGHT_ORIG", None)        # (kept on the host by this repo; all four keys hit at 512x512)
+    sch = LMSDiscreteScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear")
+    sch.set_timesteps(SCHEDULE_STEPS)
+    lat = (torch.randn(1, 4, SIZE // 8, SIZE // 8, generator=torch.manual_seed(0)) * sch.init_noise_sigma).to(device)
+    old_call, old_enabled = CrossAttention.__dict__.get("__call__"), fused_ops.ENABLED
+    CrossAttention.__call__ = eager_inj_forward
+    fused_ops.ENABLED = False
+    events = []
+
+    def on_step(i):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        events.append(e)
+
+    try:
+        n = min(SCHEDULE_STEPS, warmup + steps)
+        with torch.autocast("cuda"):
+            oracle_loop.reference_denoise_loop(unet, sch, cond, uncond, lat, weight_function, GUIDANCE,
+                                               max_steps=n, on_step=on_step)
+        torch.cuda.synchronize(device)
+    finally:
+        fused_ops.ENABLED = old_enabled
+        if old_call is None:
+            del CrossAttention.__call__
+        else:
+            CrossAttention.__call__ = old_call
+    w = min(warmup, len(events) - 2)
+    ms = events[w].elapsed_time(events[-1])
+    timed = len(events) - 1 - w
+    return {"steps_per_s": timed / (ms / 1e3), "steps": timed, "warmup": w + 1, "ms_per_step": ms / timed}
+
+
 # ------------------------------------------------------------------------------------------------
 # main arm
 # ------------------------------------------------------------------------------------------------
@@ -330,7 +522,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--quick", action="store_true", help="timed region only (for ncu launch lists): no e2e/roofline/cpu legs")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS),
+                    help="BASELINE.json config (1-based); 2 = configs[1], the one the metric is quoted on (default)")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
     rank, local_rank, world = sharding.env_world()
     if args.impl == "reference":
         run_reference_arm(args, rank)
@@ -340,7 +535,7 @@ def main():
     args.warmup = max(args.warmup, 3)
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
-    os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: one JSON line only
+    # NCCL chatter goes to stderr through _claim_stdout(); NCCL_DEBUG is left to the caller (the driver reads INFO lines)
     sharding.init_distributed("nccl")
     import torch.distributed as dist
     import paint_with_words_sd_b200 as P
@@ -349,28 +544,36 @@ def main():
 
     torch.backends.cudnn.benchmark = True
     # weights: rank 0 builds the seeded replica, everyone else receives it in one broadcast
+    ucfg = unet_config(cfg["unet"])
     if rank == 0:
-        unet = build_unet(UNetConfig.sd15(), seed=0, dtype=torch.float16, device=device)
+        unet = build_unet(ucfg, seed=0, dtype=torch.float16, device=device)
     else:
         with torch.device(device):
-            unet = P.unet.UNet2DConditionModel(UNetConfig.sd15()).half().eval().requires_grad_(False)
+            unet = P.unet.UNet2DConditionModel(ucfg).half().eval().requires_grad_(False)
     bcast_bytes = sharding.broadcast_module_weights(unet, src=0)
     unet = unet.to(memory_format=torch.channels_last)
     P.patch_unet(unet)
 
-    tok, enc = SimpleWordTokenizer(), RandomTextEncoder(768).to(device)
-    s = SETTINGS["aurora"]
-    _, _, cond, uncond = _encode_text_color_inputs(enc, tok, device, color_map_image("aurora", SIZE), dict(s["ctx"]),
-                                                   s["prompt"], "")
+    SCHED = cfg["sched_steps"]
+    wf = weight_function if args.config == 2 else make_weight_function(cfg["coef"])
+    tok, enc = SimpleWordTokenizer(), RandomTextEncoder(cfg["text_dim"]).to(device)
     sch = LMSDiscreteScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear")
-    sch.set_timesteps(SCHEDULE_STEPS)
-    lat0 = (torch.randn(1, 4, SIZE // 8, SIZE // 8, generator=torch.manual_seed(rank)) * sch.init_noise_sigma).to(device)
-    sampler = PwWSampler(unet, sch, [cond], [uncond], lat0, weight_function, GUIDANCE, use_graph=not args.no_graph)
+    sch.set_timesteps(SCHED)
+    if cfg["total_images"]:
+        if cfg["total_images"] % world:
+            raise SystemExit(f"--config {args.config} shards {cfg['total_images']} images: --gpus must divide it")
+        image_ids = sharding.shard_images(cfg["total_images"], rank, world)
+    else:
+        image_ids = [rank]
+    conds, unconds, lat0, extra = build_images(cfg, device, image_ids, tok, enc, sch)
+    m_img = len(image_ids)
+    total_images = cfg["total_images"] or world
+    sampler = PwWSampler(unet, sch, conds, unconds, lat0, wf, GUIDANCE, extra_input=extra, use_graph=not args.no_graph)
 
     def run_steps(n, per_step=None):
         done = 0
         while done < n:
-            if sampler._step_no >= SCHEDULE_STEPS:
+            if sampler._step_no >= SCHED:
                 sampler.restart(lat0)
             if per_step is not None:
                 per_step()
@@ -407,7 +610,7 @@ def main():
         per_step_launches = sampler.native_launches_per_step
         if per_step_launches is None:
             per_step_launches = (_native.launch_count - launches_before) // max(1, args.steps)
-        value = world * args.steps / (ms / 1e3)
+        value = total_images * args.steps / (ms / 1e3)        # one step = one denoising step of ONE image
 
         if args.quick:
             if rank == 0:
@@ -431,11 +634,12 @@ def main():
         lat_host.copy_(lat0)
         run_steps(3, e2e_step)
         ms_e2e = timed_region(args.steps, e2e_step)
-        e2e_value = world * args.steps / (ms_e2e / 1e3)
+        e2e_value = total_images * args.steps / (ms_e2e / 1e3)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16", "data": "synthetic", "config": workload_config(world),
+            "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if cfg["total_images"] else "weak", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic", "config": workload_config(world, args.config, m_img),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
@@ -448,23 +652,29 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peaks()
         try:
-            r2 = xattn_roofline(device, B=2, biased=1)
-            r16 = xattn_roofline(device, B=16, biased=8, iters=32)
-            ach = r2["alg_bytes"] / (r2["us_fwd"] * 1e-6) / 1e9
+            r2 = xattn_roofline(device, B=2, biased=1, dense_pair=True)
+            r16 = xattn_roofline(device, B=16, biased=8, iters=32, dense_pair=True)
+            ach = r2["alg_bytes"] / (r2["us_op"] * 1e-6) / 1e9
+            ach16 = r16["alg_bytes"] / (r16["us_op"] * 1e-6) / 1e9
             line["roofline"] = {
-                "kernel": "pww_xattn_fwd_f16 N=4096 C=320 H=8 T=77, B=2 (cond+uncond) as launched by this workload",
+                "kernel": "pww_xattn_fused_f16 (one launch: statistic + packed-map bias + softmax + PV) N=4096 C=320 H=8 "
+                          "T=77, B=2 (cond+uncond) as launched by this workload",
                 "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": ncu_traffic("B2_fwd"),
-                "traffic_note": "DRAM bytes per launch from profiles/r01_xattn_ncu_full_summary.txt (ncu --set full); below "
-                                "the algorithmic bytes because the O tile writes are still in L2 when the kernel ends",
-                "peak_source": peak_src, "us_per_launch": r2["us_fwd"], "alg_bytes_per_launch": r2["alg_bytes"],
-                "stats_kernel_us": r2["us_stats"],
-                "op_frac": r2["alg_bytes"] / ((r2["us_fwd"] + r2["us_stats"]) * 1e-6) / 1e9 / peak,
-                "batched": {"B": 16, "biased": 8, "us_fwd": r16["us_fwd"], "us_stats": r16["us_stats"],
-                            "achieved": r16["alg_bytes"] / (r16["us_fwd"] * 1e-6) / 1e9,
-                            "frac": r16["alg_bytes"] / (r16["us_fwd"] * 1e-6) / 1e9 / peak,
-                            "alg_bytes_per_launch": r16["alg_bytes"], "traffic": ncu_traffic("B16_fwd"),
-                            "op_frac": r16["alg_bytes"] / ((r16["us_fwd"] + r16["us_stats"]) * 1e-6) / 1e9 / peak},
+                "traffic": ncu_traffic("B2_fused"),
+                "peak_source": peak_src, "us_per_launch": r2["us_op"], "alg_bytes_per_launch": r2["alg_bytes"],
+                "alg_bytes_note": "SURVEY 8d formula with the PACKED map (64 B per pixel + 80 B index) instead of the "
+                                  "dense fp32 map (308 B per pixel); alg_bytes_dense_map is the round-1 figure",
+                "alg_bytes_dense_map": r2["alg_bytes_dense_map"],
+                "frac_with_dense_map_bytes": r2["alg_bytes_dense_map"] / (r2["us_op"] * 1e-6) / 1e9 / peak,
+                "op_frac": ach / peak,          # the op IS this one launch (round 1: stats launch + forward launch)
+                "dense_pair": {"us_stats": r2.get("us_dense_stats"), "us_fwd": r2.get("us_dense_fwd"),
+                               "note": "round-1 path (pww_xattn_stats_f16 + pww_xattn_fwd_f16, dense fp32 map), same inputs"},
+                "batched": {"B": 16, "biased": 8, "us_per_launch": r16["us_op"], "achieved": ach16, "frac": ach16 / peak,
+                            "alg_bytes_per_launch": r16["alg_bytes"], "traffic": ncu_traffic("B16_fused"),
+                            "alg_bytes_dense_map": r16["alg_bytes_dense_map"],
+                            "frac_with_dense_map_bytes": r16["alg_bytes_dense_map"] / (r16["us_op"] * 1e-6) / 1e9 / peak,
+                            "op_frac": ach16 / peak,
+                            "dense_pair": {"us_stats": r16.get("us_dense_stats"), "us_fwd": r16.get("us_dense_fwd")}},
                 "method": "CUDA events around a CUDA graph of back-to-back launches cycling through buffer sets > L2"}
         except Exception as e:  # keep the headline even if the micro-bench fails
             line["roofline"] = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
@@ -474,10 +684,24 @@ def main():
             line["roofline"]["eager_torch_fp16"] = {
                 "us_per_cond_uncond_pair": us,
                 "note": "reference inj_forward op sequence (heads->batch copies, QK^T, max, bias add, softmax, PV) as eager "
-                        "PyTorch fp16 on this GPU at N=4096 C=320; compare with stats_kernel_us + us_per_launch"}
+                        "PyTorch fp16 on this GPU at N=4096 C=320; compare with us_per_launch"}
         except Exception as e:
             line["roofline"]["eager_torch_fp16"] = {"error": repr(e)}
-        if world == 1 and not args.no_cpu_baseline:
+        try:    # comparison only: the reference's loop as eager fp16 PyTorch on this GPU (same weights/inputs/schedule)
+            if args.config != 2:
+                raise RuntimeError("measured for the default config only")
+            rg = reference_gpu_eager(device, steps=args.steps, warmup=3)
+            P.patch_unet(unet)
+            line["reference_gpu_eager"] = {
+                "value": rg["steps_per_s"], "unit": UNIT, "steps": rg["steps"], "warmup": rg["warmup"],
+                "ms_per_step": rg["ms_per_step"], "dtype": "f16 (torch.autocast)",
+                "what": "reference control flow on this B200: 2 batch-1 eager UNet forwards/step, inj_forward op sequence "
+                        "(paint_with_words.py:60-125) under autocast, stock PyTorch ops, no graph / caching / fused kernels",
+                "speedup_value": value / total_images / rg["steps_per_s"],
+                "speedup_e2e": e2e_value / total_images / rg["steps_per_s"]}
+        except Exception as e:
+            line["reference_gpu_eager"] = {"value": None, "error": repr(e)}
+        if world == 1 and not args.no_cpu_baseline and args.config == 2:
             try:
                 r = cpu_reference(max_timed_steps=2, warmup=0, budget_s=45.0)
                 line["cpu_baseline"] = {"value": r["steps_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",

@@ -29,8 +29,11 @@ def _workspace(device, nbytes: int) -> torch.Tensor:
 _WS_KEEP: list = []
 
 
+ENABLED = True     # bench.py's eager-PyTorch comparison leg turns the fused UNet ops off (stock PyTorch route)
+
+
 def is_fast(x: torch.Tensor) -> bool:
-    return x.is_cuda and x.dtype == torch.float16
+    return ENABLED and x.is_cuda and x.dtype == torch.float16
 
 
 def group_norm_nhwc(x: torch.Tensor, gn: torch.nn.GroupNorm, add: Optional[torch.Tensor] = None,
