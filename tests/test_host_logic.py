@@ -242,3 +242,27 @@ def test_pack_weight_map_limits():
     assert pack_weight_map(w) is not None
     w[0, 0, 0] = 1.0e5                                            # outside fp16 range
     assert pack_weight_map(w) is None
+
+
+def test_product_binary_mask_blur_and_seeded_latents_match_reference_fixtures(golden):
+    """The PRODUCT's `_get_binary_mask`, `_blur_image_mask` and `initial_latents` (paint_with_words.py:300-312, 445-455)
+    against the fixtures the unmodified reference produced (tests/golden/make_golden.py): bit-exact for the binary
+    masks and the regionally seeded latents, 1e-6 for the 39x39 Gaussian blur."""
+    from paint_with_words_sd_b200.pipeline import initial_latents
+    mb = golden["mask_builder"]
+    tok = SimpleWordTokenizer()
+    ctx = {(7, 9, 182): "aurora,0.5,-1", (136, 178, 92): "full moon,1.5,-1,4.0", (51, 193, 217): "mountains,0.4,-1",
+           (61, 163, 35): "a half-frozen lake,0.3,-1", (89, 102, 255): "boat,2.0,2077"}
+    ctx, seeds, sigmas = C._extract_seed_and_sigma_from_context(ctx)
+    assert seeds == {4: 2077} and sigmas == {1: 4.0}
+    sep, w, h = C._image_context_seperator(color_map_image("aurora"), ctx, tok)
+    masks = C._get_binary_mask(sep, seeds, torch.float32, (64, 64))
+    assert torch.equal(torch.cat(masks, 0), torch.from_numpy(mb["aurora_binary_mask"]))
+    lat = initial_latents((1, 4, 64, 64), 0, seeds, sep)
+    assert torch.equal(lat, torch.from_numpy(mb["aurora_seeded_latents"]))
+    blurred = C._blur_image_mask(list(sep), sigmas)[1][1]
+    assert torch.allclose(blurred[::8, ::8], torch.from_numpy(mb["aurora_blur_sub"]), atol=1e-6, rtol=1e-5)
+    x = blurred.double().flatten()
+    wgt = torch.arange(1, x.numel() + 1, dtype=torch.float64) % 9973
+    dig = np.array([x.sum().item(), (x * x).sum().item(), (x * wgt).sum().item()])
+    assert np.allclose(dig, mb["aurora_blur_digest"], rtol=1e-6)
