@@ -66,18 +66,20 @@ class _DeviceState:
 
     def packed(self, wmap: torch.Tensor):
         """Packed form of a dense device map, built once per (storage, version): the map is step-invariant, so the
-        torch.unique + split below runs at the first call only (outside any graph capture)."""
-        key = (wmap.data_ptr(), wmap._version, tuple(wmap.shape))
+        torch.unique + split below runs at the first call only (outside any graph capture).  The cache entry keeps a
+        reference to the dense tensor: while it is cached its storage cannot be freed and handed to a different map with
+        the same address, version and shape (which would make the key ambiguous)."""
+        key = (wmap.data_ptr(), wmap._version, tuple(wmap.shape), tuple(wmap.stride()))
         hit = self.pack_cache.get(key)
         if hit is None:
             if torch.cuda.is_current_stream_capturing():
                 raise _native.NativeError("weight map must be packed before CUDA-graph capture (run one eager step first "
                                           "or pass packed maps)")
-            if len(self.pack_cache) >= 64:
-                self.pack_cache.clear()
-            hit = pack_weight_map(wmap) or False
+            while len(self.pack_cache) >= 16:               # small FIFO: a sampler passes its own packed maps anyway
+                self.pack_cache.pop(next(iter(self.pack_cache)))
+            hit = (wmap, pack_weight_map(wmap) or False)
             self.pack_cache[key] = hit
-        return hit or None
+        return hit[1] or None
 
     def shared_index(self, batch: int) -> torch.Tensor:
         t = self.index_cache.get(batch)

@@ -331,6 +331,12 @@ int pww_debug_set_fused_grid(int grid) {
   pww::fx::debug_grid() = grid < 0 ? 0 : grid;
   return PWW_OK;
 }
+// Test infrastructure: clock64 timeline of one CTA of the fused kernel ([16][64] int64 device buffer, NULL = off).
+int pww_debug_set_fused_timeline(void* device_buffer, int cta) {
+  pww::fx::debug_timeline() = (long long*)device_buffer;
+  pww::fx::debug_timeline_cta() = cta;
+  return PWW_OK;
+}
 int pww_debug_fused_schedule(int B, int H, int tiles, int grid, const int* wmap_index, int* out, int max_jobs) {
   if (!wmap_index || !out) return PWW_ERR_BAD_ARG;
   return pww::fx::fused_schedule_host(B, H, tiles, grid, wmap_index, out, max_jobs);

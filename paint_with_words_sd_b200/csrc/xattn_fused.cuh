@@ -91,7 +91,15 @@ struct FxParams {
   const int8_t* cidx;       // [Bw, 80] dictionary column per token, -1 = none
   int tiles, units, k_batched;
   int grid;                 // CTAs (== gridDim.x): partial slots per image
+  long long* timeline;      // debug only: clock64 stamps [tag][job] of CTA `tl_cta` (see FX_TL)
+  int tl_cta;
 };
+constexpr int kFxTlTags = 16, kFxTlIts = 64;
+#define FX_TL(tag, it)                                                                                     \
+  do {                                                                                                     \
+    if (fp.timeline != nullptr && (int)blockIdx.x == fp.tl_cta && (it) >= 0 && (it) < kFxTlIts)           \
+      fp.timeline[(tag) * kFxTlIts + (it)] = clock64();                                                    \
+  } while (0)
 
 // ------------------------------------------------------------------------------------------------------------------
 // unit order (shared by the kernel and the host replay)
@@ -345,6 +353,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + C::OFF_BAR + 8 * B_TMEMPTR);
   const int nb = s_nb;
+  if (threadIdx.x == 0) FX_TL(13, 0);
   const int nu_img = p.B - nb;
   const int np = nb < nu_img ? nb : nu_img;
 
@@ -370,6 +379,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
           ptx::tma_load_4d(sb + C::NA * kQAtom + a * kKAtom, &tmk, BAR(B_QFULL + st), a * 64, jb.h, 0, kb);
         }
         if (with_map) tma_load_3d(sb + C::QKBYTES, &tmm, BAR(B_QFULL + st), 0, jb.tile * kBM, s_widx[jb.b]);
+        FX_TL(0, jb.i);
       }
     }
     __syncwarp();
@@ -417,6 +427,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
             }
           }
           const int G = (int)gridDim.x;
+          if (lane == 0) FX_TL(10, 0);
           for (int l = 0; l < nl && l < kMaxLocal; ++l) {
             const int b = lb[l];
             int expect = 0, first_c = 1 << 30;
@@ -469,6 +480,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
             }
           }
           __syncwarp();
+          if (lane == 0) FX_TL(11, 0);
           stats_ready = true;
         }
         if (jb.li != cur_li) {
@@ -503,12 +515,14 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       if (lane == 0) {
         const int st = jb.i % C::NQK, slot = jb.i % C::NS;
         ptx::mbar_wait(BAR(B_QFULL + st), (uint32_t)((jb.i / C::NQK) & 1));
+        FX_TL(1, jb.i);
         if (jb.i >= C::NS) {                           // the previous job on this slot is done with it
           const int prev = jb.i - C::NS;
           if (jb.kind == 0 || prev < ns) ptx::mbar_wait(BAR(B_SFREE + slot), (uint32_t)((prev / C::NS) & 1));
           else ptx::mbar_wait(BAR(B_PVDONE + slot), (uint32_t)(((prev - ns) / C::NS) & 1));
         }
         ptx::tc_fence_after();
+        FX_TL(2, jb.i);
         const uint32_t sb = smem0 + st * C::QKSTAGE;
 #pragma unroll
         for (int ks = 0; ks < C::KSTEPS; ++ks) {
@@ -525,6 +539,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         }
         ptx::umma_commit(BAR(B_SREADY + slot));
         ptx::umma_commit(BAR(B_QEMPTY + st));      // Q/K/map tiles are dead once S exists
+        FX_TL(3, jb.i);
       }
       __syncwarp();
     }
@@ -539,6 +554,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       if (jb.kind == 0) continue;
       const int st = jb.m % C::NV, slot = jb.i % C::NS, os = jb.i % C::NO;
       ptx::mbar_wait(BAR(B_VFULL + st), (uint32_t)((jb.m / C::NV) & 1));
+      if (lane == 0) FX_TL(7, jb.i);
       if constexpr (C::ONES) {
         unsigned char* vlast = smem_gen + C::OFF_V + st * C::VSTAGE + (C::NA - 1) * kKAtom;
         constexpr int cc = D % 64;                 // spare column inside the last atom
@@ -549,6 +565,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       }
       if (lane == 0) {
         ptx::mbar_wait(BAR(B_PREADY + slot), (uint32_t)((jb.m / C::NS) & 1));
+        FX_TL(8, jb.i);
         if (jb.m >= C::NO) ptx::mbar_wait(BAR(B_OFREE + os), (uint32_t)(((jb.m / C::NO) - 1) & 1));
         ptx::tc_fence_after();
         const uint32_t vb = smem0 + C::OFF_V + st * C::VSTAGE;
@@ -558,6 +575,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
                        ptx::make_sw128_desc(vb + ks * 16 * 128, kKAtom, 1024), idesc_pv, ks > 0);
         ptx::umma_commit(BAR(B_PVDONE + slot));
         ptx::umma_commit(BAR(B_VEMPTY + st));
+        FX_TL(9, jb.i);
       }
       __syncwarp();
     }
@@ -614,10 +632,12 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         if (jb.li != cur_li) { flush(); cur_li = jb.li; }
         ptx::mbar_wait(BAR(B_SREADY + slot), (uint32_t)((jb.i / C::NS) & 1));
         ptx::tc_fence_after();
+        if ((sw & 7) == 0 && lane == 0) FX_TL(4, jb.i);
         float s[40];
         tmem_ld40_sync(tmem_base + lane_addr + C::col_s(slot) + c * 40, s);
         ptx::tc_fence_before();
         warp_arrive(BAR(B_SFREE + slot));
+        if ((sw & 7) == 0 && lane == 0) FX_TL(5, jb.i);
         if (jb.tile * kBM + row < p.N) {
           if (p.stat == PWW_STAT_MAX) {
             // max(fp16(s)) == fp16(max(s)): rounding is monotonic, so round once at the very end
@@ -674,6 +694,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
           __threadfence();
           atomicAdd(p.counters + lbv, 1u);
         }
+        if (lane == 0) FX_TL(12, 0);
         __syncwarp();
       }
     }
@@ -741,6 +762,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         const uint32_t ts = tmem_base + lane_addr + C::col_s(slot);
         ptx::mbar_wait(BAR(B_SREADY + slot), (uint32_t)((jb.i / C::NS) & 1));
         ptx::tc_fence_after();
+        if ((sw & 7) == 0 && lane == 0) FX_TL(4, jb.i);
         float s[40];
         tmem_ld40_sync(ts + c * 40, s);
         // row max over this thread's columns (padded keys excluded), then over the row via the partner thread
@@ -782,7 +804,9 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
         warp_arrive(BAR(B_PREADY + slot));
+        if ((sw & 7) == 0 && lane == 0) FX_TL(5, jb.i);
         if (pend) epilogue();                      // overlaps with this job's P.V
+        if ((sw & 7) == 0 && lane == 0) FX_TL(6, jb.i);
         pend = 1;
         pend_slot = slot;
         pend_os = jb.i % C::NO;
@@ -801,9 +825,11 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       epilogue();
     }
     if (lane == 0) ptx::bulk_wait_group0();        // the staging tile must outlive the last store
+    if ((sw & 7) == 0 && lane == 0) FX_TL(14, g);
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) FX_TL(15, 0);
   if (warp == 1) ptx::tmem_dealloc<512>(tmem_base);
   // the last CTA to leave resets the arrival counters for the next launch (every waiter has passed its barrier)
   if (threadIdx.x == 0 && nb > 0) {
@@ -836,6 +862,14 @@ inline bool make_tmap_mpack(CUtensorMap* m, const void* base, int N, int Bw, int
   return r == CUDA_SUCCESS;
 }
 
+inline long long*& debug_timeline() {   // test infrastructure: device buffer [kFxTlTags][kFxTlIts] or null
+  static long long* t = nullptr;
+  return t;
+}
+inline int& debug_timeline_cta() {
+  static int c = 0;
+  return c;
+}
 inline int& debug_grid() {          // test infrastructure: cap the persistent grid (0 = number of SMs)
   static int g = 0;
   return g;
@@ -881,6 +915,8 @@ cudaError_t launch_fused(const XattnParams& x, const void* mpack, int64_t mpack_
   fp.units = x.B * fp.tiles * x.H;
   fp.k_batched = x.k_bs > 0 ? 1 : 0;
   fp.grid = fused_grid(fp.units);
+  fp.timeline = debug_timeline();
+  fp.tl_cta = debug_timeline_cta();
   if (!fused_range_ok(x.B, x.H, fp.tiles, fp.grid)) return cudaErrorInvalidConfiguration;
   static bool attr_set[tc::kMaxDevices] = {false};
   if (!attr_set[tc::cur_device()]) {

@@ -1,0 +1,57 @@
+"""clock64 timeline of one CTA of the one-launch kernel: python scripts/fused_timeline.py [B] [biased] [cta] [N] [H] [D]"""
+import ctypes
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from paint_with_words_sd_b200 import _native  # noqa: E402
+from paint_with_words_sd_b200 import attention as A  # noqa: E402
+from paint_with_words_sd_b200.conditioning import pack_weight_map  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+biased = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+cta = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+N = int(sys.argv[4]) if len(sys.argv) > 4 else 4096
+H = int(sys.argv[5]) if len(sys.argv) > 5 else 8
+D = int(sys.argv[6]) if len(sys.argv) > 6 else 40
+T, C = 77, H * D
+dev = "cuda"
+g = torch.Generator().manual_seed(0)
+q = (torch.randn(B, N, C, generator=g) * 0.5).half().to(dev)
+k = (torch.randn(B, T, C, generator=g) * 0.5).half().to(dev)
+v = (torch.randn(B, T, C, generator=g) * 0.5).half().to(dev)
+base = bench.golden_weight_map(N)
+if base is None:
+    base = bench.region_weight_map(N, T)
+mp0, ci0 = pack_weight_map(torch.stack([base] * max(1, biased), 0))
+pk = (mp0.to(dev), ci0.to(dev))
+idx = torch.tensor(list(range(biased)) + [-1] * (B - biased), dtype=torch.int32, device=dev)
+gs = torch.full((1,), 0.4 * math.log(8.0), dtype=torch.float32, device=dev)
+L = _native.lib()
+L.pww_debug_set_fused_timeline.argtypes = [ctypes.c_void_p, ctypes.c_int]
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+for _ in range(20):          # warm clocks
+    A.cross_attention(q, k, v, H, D ** -0.5, None, idx, _native.PWW_STAT_MAX, gs, packed=pk if biased else None)
+torch.cuda.synchronize()
+TAGS, ITS = 16, 64
+buf = torch.zeros(TAGS * ITS, dtype=torch.int64, device=dev)
+flush.fill_(1)
+torch.cuda.synchronize()
+assert L.pww_debug_set_fused_timeline(buf.data_ptr(), cta) == 0
+A.cross_attention(q, k, v, H, D ** -0.5, None, idx, _native.PWW_STAT_MAX, gs, packed=pk if biased else None)
+torch.cuda.synchronize()
+L.pww_debug_set_fused_timeline(None, 0)
+tab = buf.cpu().view(TAGS, ITS)
+t0 = int(tab[13, 0])
+f = lambda tag, it: (int(tab[tag, it]) - t0) if tab[tag, it] > 0 else -1   # noqa: E731
+print(f"B={B} biased={biased} cta={cta} N={N} H={H} D={D}; cycles since the post-prologue __syncthreads")
+print(f"grid barrier: start {f(10, 0)} end {f(11, 0)}; publish {f(12, 0)}; softmax groups done {f(14, 0)} {f(14, 1)}; kernel end {f(15, 0)}")
+print(" i | tma_issued  qfull  slot_free  s_issued | sready  math_done(pready/sfree)  epi_done | vfull  pready_seen  pv_issued")
+for it in range(ITS):
+    if tab[0, it] > 0 or tab[3, it] > 0:
+        print(f"{it:2d} | {f(0, it):7d} {f(1, it):7d} {f(2, it):7d} {f(3, it):7d} | {f(4, it):7d} {f(5, it):7d} {f(6, it):7d} | "
+              f"{f(7, it):7d} {f(8, it):7d} {f(9, it):7d}")

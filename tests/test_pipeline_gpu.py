@@ -148,6 +148,7 @@ def test_attn_processor_hook_matches_class_patch():
     from paint_with_words_sd_b200.unet import CrossAttention
     torch.manual_seed(0)
     attn = CrossAttention(320, 768, 8, 40).half().cuda()
+    attn_self = CrossAttention(320, None, 8, 40).half().cuda()
     x = (torch.randn(1, 1024, 320) * 0.5).half().cuda()
     ctx = (torch.randn(1, 77, 768) * 0.5).cuda()
     w = torch.zeros(1024, 77)
@@ -158,7 +159,7 @@ def test_attn_processor_hook_matches_class_patch():
     with torch.no_grad():
         a = PwWAttnProcessor()(attn, x, encoder_hidden_states=d)
         b = inj_forward(attn, x, d)
-        c = PwWAttnProcessor()(attn, x)                      # self-attention through the hook
+        c = PwWAttnProcessor()(attn_self, x)                 # self-attention through the hook
         e = inj_forward(attn, x, ctx)                        # tensor context: no bias
     assert torch.equal(a, b) and a.shape == x.shape and torch.isfinite(c).all()
     assert not torch.equal(a, e)                             # the bias did something

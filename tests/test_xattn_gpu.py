@@ -311,3 +311,18 @@ def test_fused_is_one_launch_and_large_bias_precision():
     assert _native.launch_count - before == 1
     ref32, _ = _oracle(q, k, v, H, D ** -0.5, w, 3.0, "max", emulate=False)
     assert (got - ref32).abs().max().item() <= 2e-3 * ref32.abs().max().item()
+
+
+def test_pack_cache_is_not_fooled_by_address_reuse():
+    """The shim caches the packed form of a dense map by storage address + version; a freed map's address is routinely
+    handed to the next map of the same shape by the caching allocator, so the cache must pin what it indexes."""
+    N, H, D, T = 1024, 8, 40, 77
+    q, k, v, w = _inputs(1, N, H, D, T, seed=31)
+    g = 0.8
+    a, _ = _run(q, k, v, H, D ** -0.5, w, g, "max")                   # w.to("cuda") is freed when _run returns
+    w2 = torch.roll(w, 7, dims=2).contiguous()                        # same shape, different columns
+    b, _ = _run(q, k, v, H, D ** -0.5, w2, g, "max")
+    ref_a, _ = _oracle(q, k, v, H, D ** -0.5, w, g, "max", emulate=False)
+    ref_b, _ = _oracle(q, k, v, H, D ** -0.5, w2, g, "max", emulate=False)
+    assert (a - ref_a).abs().max().item() <= 2e-3 * ref_a.abs().max().item()
+    assert (b - ref_b).abs().max().item() <= 2e-3 * ref_b.abs().max().item()
