@@ -5,6 +5,7 @@
 #include "pww_common.cuh"
 #include "xattn_tc.cuh"
 #include "xattn_fused.cuh"
+#include "xattn_fused2.cuh"
 #include "attn_tc.cuh"
 #include "unet_ops.cuh"
 #include <stdlib.h>
@@ -187,9 +188,18 @@ int pww_xattn_fused_f16(const void* q, const void* k, const void* v, void* out, 
   p.partials = workspace ? (pww::StatPartial*)((char*)workspace + 256) : nullptr;
   cudaStream_t s = (cudaStream_t)stream;
   // image b is biased iff it has a packed map: with mpack == NULL every index is -1 (the kernel reads wmap_index)
-  for (int b0 = 0; b0 < B; b0 += pww::fx::kMaxBatch) {            // <= 32 images per launch
+  int chunk = pww::fx::kMaxBatch;                                  // images per launch
+  if (D == 40 && pww::fx::fused_variant() == 0) {                  // grouped-head kernel: job table of <= 64 units per CTA
+    const int tiles = pww::ceil_div(N, pww::fx::kBM), hg = pww::ceil_div(H, pww::fx2::Cfg2<40>::G);
+    while (chunk > 1) {
+      const int cb = B < chunk ? B : chunk;
+      if (pww::fx2::fused2_fits(cb, hg, tiles, pww::fx::fused_grid(cb * hg * tiles))) break;
+      chunk >>= 1;
+    }
+  }
+  for (int b0 = 0; b0 < B; b0 += chunk) {
     pww::XattnParams c = p;
-    c.B = (B - b0) < pww::fx::kMaxBatch ? (B - b0) : pww::fx::kMaxBatch;
+    c.B = (B - b0) < chunk ? (B - b0) : chunk;
     c.q = p.q + (int64_t)b0 * p.q_bs;
     c.k = p.k + (int64_t)b0 * p.k_bs;
     c.v = p.v + (int64_t)b0 * p.k_bs;
@@ -207,7 +217,8 @@ int pww_xattn_fused_f16(const void* q, const void* k, const void* v, void* out, 
     c.wmap = mpack ? (const float*)mp : nullptr;                   // non-null marks "maps present" for the kernel
     cudaError_t e = cudaErrorInvalidValue;
     switch (D) {
-      case 40: e = pww::fx::launch_fused<40>(c, mp, mpack_batch_stride, Bw, ci, s); break;
+      case 40: e = pww::fx::fused_variant() == 1 ? pww::fx::launch_fused<40>(c, mp, mpack_batch_stride, Bw, ci, s)
+                                                 : pww::fx2::launch_fused2<40>(c, mp, mpack_batch_stride, Bw, ci, s); break;
       case 64: e = pww::fx::launch_fused<64>(c, mp, mpack_batch_stride, Bw, ci, s); break;
       case 80: e = pww::fx::launch_fused<80>(c, mp, mpack_batch_stride, Bw, ci, s); break;
       case 160: e = pww::fx::launch_fused<160>(c, mp, mpack_batch_stride, Bw, ci, s); break;
@@ -335,6 +346,22 @@ int pww_debug_set_fused_grid(int grid) {
 int pww_debug_set_fused_timeline(void* device_buffer, int cta) {
   pww::fx::debug_timeline() = (long long*)device_buffer;
   pww::fx::debug_timeline_cta() = cta;
+  return PWW_OK;
+}
+// Test infrastructure: 0 = grouped-head kernel at D = 40 (default), 1 = per-head one-launch kernel at every head dim (A/B timing).
+int pww_debug_set_fused_variant(int v) {
+  if (v != 0 && v != 1) return PWW_ERR_BAD_ARG;
+  pww::fx::fused_variant() = v;
+  return PWW_OK;
+}
+// Host replay of the grouped-head kernel's job lists (14 int32 per job, see fused2_schedule_host).
+int pww_debug_fused2_schedule(int B, int H, int G, int tiles, int grid, const int* wmap_index, int* out, int max_jobs) {
+  if (!wmap_index || !out) return PWW_ERR_BAD_ARG;
+  return pww::fx2::fused2_schedule_host(B, H, G, tiles, grid, wmap_index, out, max_jobs);
+}
+// Test infrastructure: device buffer of grid * (2 + 1024) uint32 the grouped-head kernel copies every CTA's job table to.
+int pww_debug_set_fused_jobs_dump(void* device_buffer) {
+  pww::fx::debug_jobs_dump() = (unsigned*)device_buffer;
   return PWW_OK;
 }
 int pww_debug_fused_schedule(int B, int H, int tiles, int grid, const int* wmap_index, int* out, int max_jobs) {

@@ -93,6 +93,8 @@ struct FxParams {
   int grid;                 // CTAs (== gridDim.x): partial slots per image
   long long* timeline;      // debug only: clock64 stamps [tag][job] of CTA `tl_cta` (see FX_TL)
   int tl_cta;
+  int hg;                   // head groups per row tile (grouped-head kernel, xattn_fused2.cuh)
+  unsigned* jobs_dump;      // debug only: [grid][2 + 2 * 512] = njobs, nstat, job table of every CTA (grouped-head kernel)
 };
 constexpr int kFxTlTags = 16, kFxTlIts = 64;
 #define FX_TL(tag, it)                                                                                     \
@@ -870,6 +872,14 @@ inline int& debug_timeline_cta() {
   static int c = 0;
   return c;
 }
+inline unsigned*& debug_jobs_dump() {   // test infrastructure: device buffer the grouped-head kernel copies its job tables to
+  static unsigned* p = nullptr;
+  return p;
+}
+inline int& fused_variant() {        // 0 = grouped-head kernel at D = 40, 1 = per-head kernel everywhere (A/B timing)
+  static int v = 0;
+  return v;
+}
 inline int& debug_grid() {          // test infrastructure: cap the persistent grid (0 = number of SMs)
   static int g = 0;
   return g;
@@ -917,6 +927,8 @@ cudaError_t launch_fused(const XattnParams& x, const void* mpack, int64_t mpack_
   fp.grid = fused_grid(fp.units);
   fp.timeline = debug_timeline();
   fp.tl_cta = debug_timeline_cta();
+  fp.hg = x.H;
+  fp.jobs_dump = nullptr;
   if (!fused_range_ok(x.B, x.H, fp.tiles, fp.grid)) return cudaErrorInvalidConfiguration;
   static bool attr_set[tc::kMaxDevices] = {false};
   if (!attr_set[tc::cur_device()]) {

@@ -1,0 +1,907 @@
+// Paint-with-Words cross-attention, ONE launch, head-dim 40 (the 64x64-latent level of SD1.5: N = 4096, 8 heads of 40).
+//
+// Same math, barrier rules, softmax / P.V / epilogue code and packed-map bias as xattn_fused.cuh (read its header first);
+// what changes is HOW Q REACHES SHARED MEMORY.  A head slice of a query row is 80 bytes at an 80-byte offset, and the TMA
+// engine streams such rows at ~1100-1300 cycles per [128 x 80 B] box per SM whatever the ring depth (1.9 TB/s over the
+// chip, scripts/tma_probe.cu / profiles/r02_tma_probe.txt) -- the one-launch kernel was bound by exactly that.  Full
+// 128-byte lines stream 1.6-2x faster, so here
+//     work unit = (image, 128-row tile, group of G = 4 heads);  Q tile = [128 rows x 192 columns] = 3 swizzle atoms of
+//                 whole 128-byte lines covering the unit's 160 columns, loaded ONCE per unit pass and shared by its heads;
+//     S_h       = Q[:, 16-column blocks covering head h] . K'_h^T with 3 k-steps whose A descriptors point INTO the shared
+//                 Q tile.  Head h starts at column 40 h, i.e. 0 or 8 columns into its first block, so the K operand of an
+//                 odd head is loaded 8 columns to the right (TMA box at d = -8: out-of-bounds columns are zero-filled on
+//                 both sides), and the neighbouring heads' Q columns inside the blocks meet zeros.
+// A CTA whose whole unit range fits the Q ring (<= 2 units: the cond + uncond launch of the denoising loop puts at most
+// one unit on a CTA) keeps its Q tiles resident: the statistic pass and the softmax pass read Q from HBM once.
+// K and V tiles of a head ([80 x 64] fp16 atoms) travel in their own rings, per job, from L2.
+#pragma once
+#include "ptx_sm100.cuh"
+#include "pww_common.cuh"
+#include "xattn_tc.cuh"   // make_tmap, make_tmap_out, encode_fn, num_sms, tc_error_buf
+#include "xattn_fused.cuh"   // FxWalk, fx_range, fx_cta_has_image, PTX helpers, debug knobs
+
+namespace pww {
+namespace fx2 {
+using namespace fx;   // unit walk, helpers and constants shared with the per-head kernel
+
+template <int D>
+struct Cfg2 {
+  static_assert(D == 40, "the grouped-head kernel is built for head dim 40");
+  static constexpr int G = 4;                       // heads per unit: G * D = 160 columns
+  static constexpr int NAQ = 3;                     // 64-column atoms of the unit's Q tile (192 columns cover the 160)
+  static constexpr int DP = (D + 15) / 16 * 16;
+  static constexpr int KSTEPS = DP / 16;            // 16-column blocks per head: 3 (a head starts 0 or 8 columns into its first block)
+  static constexpr bool ONES = true;                // row sums ride on the P.V UMMA (spare V column = 1.0)
+  static constexpr int DPV = (D + 16) / 16 * 16;    // UMMA N of P.V: 48
+  static constexpr int NS = 4;                      // score slots (80 fp32 columns each; P overwrites the S it came from)
+  static constexpr int NO = 4;                      // output accumulators (48 columns each)
+  static constexpr uint32_t O_STRIDE = DPV;
+  __host__ __device__ static constexpr uint32_t col_s(int slot) { return (uint32_t)slot * 80u; }
+  __host__ __device__ static constexpr uint32_t col_o(int os) { return (uint32_t)NS * 80u + (uint32_t)os * O_STRIDE; }
+  static_assert(NS * 80 + NO * DPV <= 512, "TMEM budget");
+  static constexpr int NQ = 2;                      // Q ring: unit passes in flight (or resident units)
+  static constexpr int NK = 3;                      // K ring: jobs in flight
+  static constexpr int NV = 3;                      // V ring: main jobs in flight
+  static constexpr uint32_t QBYTES = NAQ * kQAtom;
+  static constexpr uint32_t QSTAGE = QBYTES + kMAtom;           // 3 Q atoms | packed-map atom of the row tile
+  static constexpr uint32_t KSTAGE = kKAtom, VSTAGE = kKAtom;
+  static constexpr int C0 = 24, C1 = D - C0;        // output columns of the two threads of a row (multiples of 8)
+  static constexpr int EPI_W = C0;
+  static constexpr int EPI_NPASS = 1;
+  static constexpr uint32_t STG_WARP = 32 * EPI_W * 2;
+  static constexpr uint32_t OFF_K = NQ * QSTAGE;
+  static constexpr uint32_t OFF_V = OFF_K + NK * KSTAGE;
+  static constexpr uint32_t OFF_COEF = OFF_V + NV * VSTAGE;     // 2 B-operand tiles [80 x 32 fp16], 64-byte-swizzled rows
+  static constexpr uint32_t OFF_STG = OFF_COEF + 2 * kCoefTile;
+  static constexpr uint32_t OFF_XCHG = OFF_STG + 16 * STG_WARP; // [group][buf][half][128] fp32 row maxima
+  static constexpr uint32_t OFF_BAR = OFF_XCHG + 2 * 2 * 2 * 128 * 4 * 2;
+  static constexpr uint32_t SMEM = OFF_BAR + 512 + 1024;        // + alignment slack
+  static_assert(SMEM <= 232448 - 8192, "shared memory budget (dynamic + static tables incl. the 4 KB job table)");
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// job lists (shared by the kernel and the host replay)
+// ------------------------------------------------------------------------------------------------------------------
+// Units are walked with the per-head kernel's FxWalk, "heads" being head GROUPS (hg = ceil(H / G) of them); a unit
+// expands into one job per head of its group.  A CTA runs three passes over its contiguous unit range, as in the
+// per-head kernel: statistic jobs of the biased units, softmax jobs of the unbiased units, softmax jobs of the biased
+// units.  `up` numbers the unit passes in processing order (Q ring), `ul` is the unit's position in the CTA's range.
+struct Fx2Job {
+  int b, h, tile, biased, gi;
+  int kind;     // 0 = stat, 1 = main
+  int i;        // job index (score slot = i % NS, softmax group = i % 2, K stage = i % NK)
+  int m;        // main-job index (V stage = m % NV), -1 for stat jobs
+  int li;       // local index of the biased image inside this CTA's range (biased jobs)
+  int up, ul;   // unit pass / local unit
+  int first, last;   // first / last job of its unit pass
+};
+struct Fx2Jobs {
+  FxWalk w;
+  int u0, n_units, B, H, HG, G, tiles, nb;
+  const int* img;
+  int it, phase, i, m, li, lastb, up;
+  FxUnit cur;
+  int cur_ul, cur_up, cur_li, hl, nh;
+  bool have;
+  __host__ __device__ __forceinline__ Fx2Jobs(int u0_, int n_units_, int B_, int H_, int G_, int tiles_, int nb_,
+                                              const int* img_)
+      : u0(u0_), n_units(n_units_), B(B_), H(H_), G(G_), tiles(tiles_), nb(nb_), img(img_) {
+    HG = (H + G - 1) / G;
+    phase = nb > 0 ? 0 : 1;
+    i = 0; m = 0; up = 0;
+    rewind();
+  }
+  __host__ __device__ __forceinline__ void rewind() {
+    w = FxWalk(u0, B, HG, tiles, nb, img);
+    it = 0; li = -1; lastb = -1; have = false;
+  }
+  __host__ __device__ __forceinline__ bool next(Fx2Job& jb) {
+    for (;;) {
+      if (have) {
+        jb.b = cur.b; jb.h = cur.h * G + hl; jb.tile = cur.tile; jb.biased = cur.biased; jb.gi = cur.gi;
+        jb.kind = phase == 0 ? 0 : 1;
+        jb.i = i++;
+        jb.m = phase == 0 ? -1 : m++;
+        jb.li = cur.biased ? cur_li : -1;
+        jb.up = cur_up; jb.ul = cur_ul;
+        jb.first = hl == 0; jb.last = hl == nh - 1;
+        if (++hl == nh) have = false;
+        return true;
+      }
+      while (it < n_units) {
+        const FxUnit u = w.get();
+        w.next();
+        const int ul = it++;
+        if (u.biased && u.b != lastb) { ++li; lastb = u.b; }
+        const bool want = (phase == 1) ? !u.biased : (u.biased != 0);
+        if (!want) continue;
+        cur = u; cur_ul = ul; cur_li = li; cur_up = up++;
+        hl = 0;
+        nh = H - u.h * G < G ? H - u.h * G : G;
+        have = true;
+        break;
+      }
+      if (have) continue;
+      if (phase == 2) return false;
+      ++phase;
+      rewind();
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------------------------
+// Job table.  One warp builds the CTA's job list in shared memory during the prologue (parallel over the units of the
+// range: ballots and warp scans, no sequential walk) and every role then runs a WARP-UNIFORM loop over it.  That matters
+// more than it looks: tcgen05.mma, the TMA instructions and tcgen05.commit take their operands from uniform registers, and
+// a loop driven by one lane (`if (lane == 0)`) makes the compiler wrap every such instruction in an R2UR "waterfall" loop
+// (~30 instructions, 100-250 cycles per issue; measured on the first version of this kernel: ~2000 cycles of issuing
+// thread per job).  With the whole warp running the loop and `elect.sync` guarding only the issue, the descriptors are
+// computed on the uniform datapath and the UMMAs of a job go out back to back.
+//   s_jobs[i].x = b | h << 8 | tile << 16          s_jobs[i].y = flags, see the JF_* masks
+constexpr int kMaxUnits = 64;        // units per CTA (host-checked: the C ABI splits larger batches)
+constexpr int kMaxJobs = 512;        // kMaxUnits * G heads * 2 passes
+constexpr uint32_t JF_MAIN = 1u, JF_BIASED = 2u, JF_FIRST = 4u, JF_LAST = 8u;   // | li << 4 (2 bits) | ul << 8 (8 bits)
+
+__device__ __forceinline__ bool elect_one() {     // true on exactly one lane of a converged warp
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+template <int D, int TT>
+__global__ void __launch_bounds__(kThreads, 1)
+xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
+                    const __grid_constant__ CUtensorMap tmv, const __grid_constant__ CUtensorMap tmm,
+                    const __grid_constant__ CUtensorMap tmo0, const __grid_constant__ CUtensorMap tmo1,
+                    const FxParams fp) {
+  using C = Cfg2<D>;
+  const XattnParams& p = fp.x;
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  unsigned char* smem_gen = smem_raw + (smem0 - ptx::smem_u32(smem_raw));
+  const uint32_t bar0 = smem0 + C::OFF_BAR;
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  constexpr int B_QFULL = 0, B_QEMPTY = 2, B_KFULL = 4, B_KEMPTY = 7, B_VFULL = 10, B_VEMPTY = 13, B_SREADY = 16,
+                B_SFREE = 20, B_PREADY = 24, B_PVDONE = 28, B_OFREE = 32, B_COEF = 36, B_TMEMPTR = 38;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = TT ? TT : p.T;
+  int u0, u1;
+  fx_range(blockIdx.x, gridDim.x, fp.units, u0, u1);
+  const int n_it = u1 - u0;
+  // Resident mode: the CTA's whole unit range fits the Q ring, so unit ul owns stage ul for the whole kernel (loaded once,
+  // read by the statistic pass AND the softmax pass); otherwise a stage is loaded per unit pass and released after it.
+  const bool resident = n_it <= C::NQ;
+  const int HG = fp.hg;
+
+  __shared__ int s_widx[kMaxBatch];
+  __shared__ int s_img[kMaxBatch];                // biased images first, then unbiased
+  __shared__ int s_nb, s_njobs, s_nstat, s_nl;
+  __shared__ int s_lb[kMaxLocal], s_lp[kMaxLocal];   // image / group position of the CTA's local biased images
+  __shared__ float s_coef[kMaxLocal];             // g(sigma) * statistic of the CTA's local biased images
+  __shared__ StatPartial s_part[16][kMaxLocal];   // [softmax warp][local biased image]
+  __shared__ uint2 s_jobs[kMaxJobs];
+
+  if (warp == 2) {
+    // ---- stable partition of the images by "has a weight map" ----
+    {
+      const int b = lane;
+      const int wi = (b < p.B && p.wmap != nullptr) ? (p.wmap_index ? p.wmap_index[b] : b) : -1;   // wmap == NULL: no maps at all
+      const bool valid = b < p.B, bi = valid && wi >= 0;
+      const unsigned mb = __ballot_sync(0xffffffffu, bi), mu = __ballot_sync(0xffffffffu, valid && !bi);
+      const unsigned lt = (1u << lane) - 1u;
+      const int nbt = __popc(mb);
+      if (bi) s_img[__popc(mb & lt)] = b;
+      else if (valid) s_img[nbt + __popc(mu & lt)] = b;
+      if (valid) s_widx[b] = wi;
+      if (lane == 0) s_nb = nbt;
+    }
+    __syncwarp();
+    // ---- job table: pass 1 gives every unit its place in the three lists, pass 2 expands units into head jobs ----
+    const int nbi = s_nb;
+    const unsigned lt = (1u << lane) - 1u;
+    uint4* s_unit = reinterpret_cast<uint4*>(smem_gen + C::OFF_STG);     // scratch: the staging tiles are idle until the first epilogue
+    int c_sj = 0, c_uj = 0, c_li = -1, c_lastb = -1;
+    for (int base = 0; base < n_it; base += 32) {
+      const int ul = base + lane;
+      const bool valid = ul < n_it;
+      FxUnit u;
+      u.b = 0; u.h = 0; u.tile = 0; u.biased = 0; u.gi = 0;
+      if (valid) u = FxWalk(u0 + ul, p.B, HG, fp.tiles, nbi, s_img).get();
+      const bool isb = valid && u.biased, isu = valid && !u.biased;
+      const unsigned mb = __ballot_sync(0xffffffffu, isb);
+      const unsigned prev = mb & lt;
+      const int pl = prev ? 31 - __clz(prev) : 0;
+      int bprev = __shfl_sync(0xffffffffu, u.b, pl);
+      if (!prev) bprev = c_lastb;
+      const bool newimg = isb && u.b != bprev;
+      const unsigned mn = __ballot_sync(0xffffffffu, newimg);
+      const int li = c_li + __popc(mn & (lt | (1u << lane)));
+      const int nh = valid ? ((p.H - u.h * C::G) < C::G ? (p.H - u.h * C::G) : C::G) : 0;
+      int sb = isb ? nh : 0, su = isu ? nh : 0;            // inclusive warp scans of the head counts
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int tb = __shfl_up_sync(0xffffffffu, sb, o), tu = __shfl_up_sync(0xffffffffu, su, o);
+        if (lane >= o) { sb += tb; su += tu; }
+      }
+      const int joff = isb ? c_sj + sb - nh : c_uj + su - nh;
+      if (valid) s_unit[ul] = make_uint4((unsigned)u.b | ((unsigned)u.h << 8) | ((unsigned)u.tile << 16),
+                                         (unsigned)u.biased | ((unsigned)(li < 0 ? 0 : li) << 4) | ((unsigned)nh << 8),
+                                         (unsigned)joff, 0u);
+      if (newimg && li < kMaxLocal) { s_lb[li] = u.b; s_lp[li] = u.gi; }
+      c_sj += __shfl_sync(0xffffffffu, sb, 31);
+      c_uj += __shfl_sync(0xffffffffu, su, 31);
+      c_li += __popc(mn);
+      if (mb) c_lastb = __shfl_sync(0xffffffffu, u.b, 31 - __clz(mb));
+    }
+    __syncwarp();
+    const int ns = c_sj, nuj = c_uj;
+    for (int ul = lane; ul < n_it; ul += 32) {
+      const uint4 r = s_unit[ul];
+      const unsigned bi = r.y & 1u, li = (r.y >> 4) & 3u, nh = (r.y >> 8) & 0xffu, hg = (r.x >> 8) & 0xffu;
+      const unsigned base_x = (r.x & 0xffu) | (r.x & 0xffff0000u);
+      for (unsigned hl = 0; hl < nh; ++hl) {
+        const unsigned x = base_x | ((hg * C::G + hl) << 8);
+        const unsigned fl = (hl == 0 ? JF_FIRST : 0u) | (hl == nh - 1 ? JF_LAST : 0u) | (li << 4) | ((unsigned)(ul & 0xff) << 8);
+        if (bi) {
+          s_jobs[r.z + hl] = make_uint2(x, fl | JF_BIASED);
+          s_jobs[ns + nuj + r.z + hl] = make_uint2(x, fl | JF_BIASED | JF_MAIN);
+        } else {
+          s_jobs[ns + r.z + hl] = make_uint2(x, fl | JF_MAIN);
+        }
+      }
+    }
+    if (lane == 0) { s_njobs = 2 * ns + nuj; s_nstat = ns; s_nl = c_li + 1; }
+  }
+  for (int i = threadIdx.x; i < 16 * kMaxLocal; i += kThreads) {
+    StatPartial sp;
+    sp.vmax = -INFINITY; sp.sum = 0.0; sp.sumsq = 0.0; sp.pad = 0.0;
+    s_part[i / kMaxLocal][i % kMaxLocal] = sp;
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmq);
+    ptx::prefetch_tmap(&tmk);
+    ptx::prefetch_tmap(&tmv);
+    ptx::prefetch_tmap(&tmm);
+    ptx::prefetch_tmap(&tmo0);
+    ptx::prefetch_tmap(&tmo1);
+    for (int s = 0; s < C::NQ; ++s) {
+      ptx::mbar_init(BAR(B_QFULL + s), 1);
+      ptx::mbar_init(BAR(B_QEMPTY + s), 1);
+    }
+    for (int s = 0; s < 3; ++s) {
+      ptx::mbar_init(BAR(B_KFULL + s), 1);
+      ptx::mbar_init(BAR(B_KEMPTY + s), 1);
+      ptx::mbar_init(BAR(B_VFULL + s), 1);
+      ptx::mbar_init(BAR(B_VEMPTY + s), 1);
+    }
+    for (int s = 0; s < 4; ++s) {
+      ptx::mbar_init(BAR(B_SREADY + s), 1);
+      ptx::mbar_init(BAR(B_SFREE + s), 8);       // one elected arrive per warp of the slot's softmax group
+      ptx::mbar_init(BAR(B_PREADY + s), 8);
+      ptx::mbar_init(BAR(B_PVDONE + s), 1);
+      ptx::mbar_init(BAR(B_OFREE + s), 8);
+    }
+    ptx::mbar_init(BAR(B_COEF + 0), 1);
+    ptx::mbar_init(BAR(B_COEF + 1), 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<512>(BAR(B_TMEMPTR));
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + C::OFF_BAR + 8 * B_TMEMPTR);
+  const int nb = s_nb;
+  const int njobs = s_njobs, ns = s_nstat;
+  if (threadIdx.x == 0) FX_TL(13, 0);
+  if (fp.jobs_dump != nullptr) {                              // debug: the job table as built on the device
+    unsigned* d = fp.jobs_dump + (size_t)blockIdx.x * (2 + 2 * kMaxJobs);
+    if (threadIdx.x == 0) { d[0] = (unsigned)njobs; d[1] = (unsigned)ns; }
+    for (int i = threadIdx.x; i < njobs; i += kThreads) { d[2 + 2 * i] = s_jobs[i].x; d[3 + 2 * i] = s_jobs[i].y; }
+  }
+  const int nu_img = p.B - nb;
+  const int np = nb < nu_img ? nb : nu_img;
+
+  if (blockIdx.x == 0 && p.stats_out != nullptr)            // images without a weight map report statistic 0
+    for (int b = threadIdx.x; b < p.B; b += kThreads)
+      if (s_widx[b] < 0) p.stats_out[b] = 0.f;
+
+  if (warp == 0) {
+    // ============================== TMA producer: Q (+ packed map) per unit pass, K per job ==============================
+    auto load_q = [&](int qst, int b, int tile, int hgi, bool with_map) {     // elected lane only
+      const uint32_t qb = smem0 + qst * C::QSTAGE;
+      ptx::mbar_arrive_expect_tx(BAR(B_QFULL + qst), C::QBYTES + (with_map ? kMAtom : 0u));
+      const int atom0 = (hgi * C::G * D) / 64;             // first 64-column atom of the unit's heads
+#pragma unroll
+      for (int a = 0; a < C::NAQ; ++a)
+        tma_load_3d(qb + a * kQAtom, &tmq, BAR(B_QFULL + qst), (atom0 + a) * 64, tile * kBM, b);
+      if (with_map) tma_load_3d(qb + C::QBYTES, &tmm, BAR(B_QFULL + qst), 0, tile * kBM, s_widx[b]);
+    };
+    if (resident) {                                // every unit of the range owns a stage: all loads go out now
+      unsigned loaded = 0;
+      for (int i = 0; i < njobs; ++i) {
+        const uint2 r = s_jobs[i];
+        const int ul = (r.y >> 8) & 0xff;
+        if ((r.y & JF_FIRST) && !((loaded >> ul) & 1u)) {
+          loaded |= 1u << ul;
+          if (elect_one()) {
+            load_q(ul, r.x & 0xff, r.x >> 16, (int)((r.x >> 8) & 0xff) / C::G, (r.y & JF_BIASED) != 0);
+            FX_TL(0, i);
+          }
+          __syncwarp();
+        }
+      }
+    }
+    int up = -1;
+    for (int i = 0; i < njobs; ++i) {
+      const uint2 r = s_jobs[i];
+      const int b = r.x & 0xff, h = (r.x >> 8) & 0xff, tile = r.x >> 16;
+      if (r.y & JF_FIRST) {
+        ++up;
+        if (!resident) {                             // ring mode: one load per unit pass
+          const int qst = up % C::NQ;
+          ptx::mbar_wait(BAR(B_QEMPTY + qst), (uint32_t)(((up / C::NQ) & 1) ^ 1));
+          if (elect_one()) {
+            // the packed map of the row tile rides with Q in the pass that reads it
+            load_q(qst, b, tile, h / C::G, (r.y & (JF_BIASED | JF_MAIN)) == (JF_BIASED | JF_MAIN));
+            FX_TL(0, i);
+          }
+          __syncwarp();
+        }
+      }
+      const int st = i % C::NK;
+      ptx::mbar_wait(BAR(B_KEMPTY + st), (uint32_t)(((i / C::NK) & 1) ^ 1));
+      if (elect_one()) {
+        ptx::mbar_arrive_expect_tx(BAR(B_KFULL + st), C::KSTAGE);
+        // K'_h: the head's 40 columns placed 0 or 8 columns into the tile (see the header); the rest is TMA zero fill
+        ptx::tma_load_4d(smem0 + C::OFF_K + st * C::KSTAGE, &tmk, BAR(B_KFULL + st), -((h * D) % 16), h, 0,
+                         fp.k_batched ? b : 0);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 2) {
+    // ============================== TMA producer: V tiles of the main jobs ==============================
+    for (int i = ns; i < njobs; ++i) {
+      const uint2 r = s_jobs[i];
+      const int m = i - ns, st = m % C::NV;
+      ptx::mbar_wait(BAR(B_VEMPTY + st), (uint32_t)(((m / C::NV) & 1) ^ 1));
+      if (elect_one()) {
+        ptx::mbar_arrive_expect_tx(BAR(B_VFULL + st), C::VSTAGE);
+        ptx::tma_load_4d(smem0 + C::OFF_V + st * C::VSTAGE, &tmv, BAR(B_VFULL + st), 0, (r.x >> 8) & 0xff, 0,
+                         fp.k_batched ? (int)(r.x & 0xff) : 0);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ============================== UMMA issuer: S of every job (+ grid barrier and the bias operand) ==============================
+    constexpr uint32_t idesc_qk = ptx::make_idesc_f16(128, kTP, false, false);
+    bool stats_ready = false;
+    int cur_li = -1, up = -1;
+    for (int i = 0; i < njobs; ++i) {
+      const uint2 r = s_jobs[i];
+      const int b = r.x & 0xff, h = (r.x >> 8) & 0xff;
+      const bool is_main = (r.y & JF_MAIN) != 0, biased = (r.y & JF_BIASED) != 0;
+      const int li = (r.y >> 4) & 3, ul = (r.y >> 8) & 0xff;
+      if (r.y & JF_FIRST) ++up;
+      if (is_main && biased) {
+        if (!stats_ready) {
+          // ---- grid barrier: every CTA owning units of my biased images has published its partial ----
+          const int nl = s_nl;
+          const int G = (int)gridDim.x;
+          if (lane == 0) FX_TL(10, 0);
+          for (int l = 0; l < nl && l < kMaxLocal; ++l) {
+            const int bl = s_lb[l], pos = s_lp[l];
+            int expect = 0, first_c = 1 << 30;
+            for (int c = lane; c < G; c += 32)
+              if (fx_cta_has_image(c, G, fp.units, pos, HG, fp.tiles, np)) { ++expect; if (c < first_c) first_c = c; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              expect += __shfl_xor_sync(0xffffffffu, expect, o);
+              first_c = min(first_c, __shfl_xor_sync(0xffffffffu, first_c, o));
+            }
+            if (lane == 0) {
+              const long long t0 = clock64();
+              while (ld_acquire_gpu(p.counters + bl) < (unsigned)expect) {
+                __nanosleep(32);
+                if (clock64() - t0 > 20000000000LL) {
+                  printf("pww: grid barrier timeout block %d image %d have %u want %d\n", blockIdx.x, bl,
+                         ld_acquire_gpu(p.counters + bl), expect);
+                  __trap();
+                }
+              }
+            }
+            __syncwarp();
+            (void)ld_acquire_gpu(p.counters + bl);                 // every lane orders its partial loads behind the counter
+            double m = -INFINITY, a = 0.0, q = 0.0;
+            for (int c = lane; c < G; c += 32)
+              if (fx_cta_has_image(c, G, fp.units, pos, HG, fp.tiles, np)) {
+                const StatPartial* pp = p.partials + (int64_t)bl * G + c;
+                m = fmax(m, __ldcg(&pp->vmax));
+                a += __ldcg(&pp->sum);
+                q += __ldcg(&pp->sumsq);
+              }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+              a += __shfl_xor_sync(0xffffffffu, a, o);
+              q += __shfl_xor_sync(0xffffffffu, q, o);
+            }
+            if (lane == 0) {
+              const double cnt = (double)p.H * (double)p.N * (double)p.T;
+              double rr;
+              if (p.stat == PWW_STAT_MAX) {
+                rr = m;
+              } else {
+                const double var = (q - a * a / cnt) / (cnt - 1.0);
+                rr = sqrt(var > 0.0 ? var : 0.0);
+              }
+              const float st16 = round_to_f16((float)rr);         // qk.max() / qk.std() return fp16 in the reference
+              s_coef[l] = __ldg(p.g_sigma) * st16;
+              if (first_c == (int)blockIdx.x && p.stats_out != nullptr) p.stats_out[bl] = st16;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) FX_TL(11, 0);
+          stats_ready = true;
+        }
+        if (li != cur_li) {
+          // ---- B operand of the bias k-steps for this image: [80 tokens x 32] fp16, 64-byte-swizzled rows ----
+          const int buf = li & 1;
+          if (cur_li >= 0) {                                       // UMMAs reading the old tile
+            if (elect_one()) ptx::umma_commit(BAR(B_COEF + (cur_li & 1)));
+            __syncwarp();
+          }
+          if (li >= 2) ptx::mbar_wait(BAR(B_COEF + buf), (uint32_t)(((li >> 1) - 1) & 1));
+          const float x = s_coef[li < kMaxLocal ? li : 0];
+          const __half xh = __float2half_rn(x);
+          const __half xl = __float2half_rn(x - __half2float(xh));
+          unsigned char* tile = smem_gen + C::OFF_COEF + buf * kCoefTile;
+          const int8_t* ci = fp.cidx + (int64_t)s_widx[b] * kTP;
+          for (int t = lane; t < kTP; t += 32) {
+            uint4* rowp = reinterpret_cast<uint4*>(tile + t * 64);
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) rowp[ch] = make_uint4(0, 0, 0, 0);
+            const int rc = (t < T) ? (int)ci[t] : -1;
+            if (rc >= 0 && rc < kRC) {
+              auto put = [&](int k, __half v) {
+                *reinterpret_cast<__half*>(tile + t * 64 + ((((k >> 3) ^ ((t >> 1) & 3))) << 4) + (k & 7) * 2) = v;
+              };
+              put(rc, xh);
+              put(kRC + rc, xh);
+              put(2 * kRC + rc, xl);
+            }
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          cur_li = li;
+        }
+      }
+      const int kst = i % C::NK, slot = i % C::NS;
+      const int qst = resident ? ul : up % C::NQ;
+      // resident stages complete exactly one phase; ring stages one phase per unit pass
+      ptx::mbar_wait(BAR(B_QFULL + qst), resident ? 0u : (uint32_t)((up / C::NQ) & 1));
+      ptx::mbar_wait(BAR(B_KFULL + kst), (uint32_t)((i / C::NK) & 1));
+      if (lane == 0) FX_TL(1, i);
+      if (i >= C::NS) {                              // the previous job on this slot is done with it
+        const int prev = i - C::NS;
+        if (!is_main || prev < ns) ptx::mbar_wait(BAR(B_SFREE + slot), (uint32_t)((prev / C::NS) & 1));
+        else ptx::mbar_wait(BAR(B_PVDONE + slot), (uint32_t)(((prev - ns) / C::NS) & 1));
+      }
+      ptx::tc_fence_after();
+      if (lane == 0) FX_TL(2, i);
+      const uint32_t qb = smem0 + qst * C::QSTAGE, kb = smem0 + C::OFF_K + kst * C::KSTAGE;
+      const int atom0 = ((h / C::G) * C::G * D) / 64;
+      const int blk0 = (h * D) / 16;                 // first 16-column block of the head inside the query row
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < C::KSTEPS; ++ks) {
+          const int blk = blk0 + ks;
+          const uint32_t qa = qb + (uint32_t)(blk / 4 - atom0) * kQAtom + (uint32_t)(blk % 4) * 32u;
+          ptx::umma_ss(tmem_base + C::col_s(slot), ptx::make_sw128_desc(qa, 16, 1024),
+                       ptx::make_sw128_desc(kb + ks * 32, 16, 1024), idesc_qk, ks > 0);
+        }
+        if (is_main && biased) {
+          const uint32_t ma = qb + C::QBYTES, ca = smem0 + C::OFF_COEF + (li & 1) * kCoefTile;
+#pragma unroll
+          for (int ks = 0; ks < kMW / 16; ++ks)
+            ptx::umma_ss(tmem_base + C::col_s(slot), make_sw64_desc(ma + ks * 32), make_sw64_desc(ca + ks * 32), idesc_qk, true);
+        }
+        ptx::umma_commit(BAR(B_SREADY + slot));
+        ptx::umma_commit(BAR(B_KEMPTY + kst));       // the K tile is dead once S exists
+        if ((r.y & JF_LAST) && !resident) ptx::umma_commit(BAR(B_QEMPTY + qst));   // ... and so is the unit's Q tile after its last head
+        FX_TL(3, i);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 3) {
+    // ============================== UMMA issuer: O = P V of every main job ==============================
+    // The whole warp waits for the V tile (every VFULL phase observed by the same threads, in order) and sets the spare
+    // column of the V atom to 1.0 for every real token: accumulator column D is the row sum.
+    constexpr uint32_t idesc_pv = ptx::make_idesc_f16(128, C::DPV, false, true);
+    for (int i = ns; i < njobs; ++i) {
+      const int m = i - ns;
+      const int st = m % C::NV, slot = i % C::NS, os = i % C::NO;
+      ptx::mbar_wait(BAR(B_VFULL + st), (uint32_t)((m / C::NV) & 1));
+      if (lane == 0) FX_TL(7, i);
+      {
+        unsigned char* vlast = smem_gen + C::OFF_V + st * C::VSTAGE;
+        constexpr int cc = D % 64;                 // spare column inside the atom
+        for (int rr = lane; rr < T; rr += 32)
+          *reinterpret_cast<__half*>(vlast + rr * 128 + ((((cc >> 3) ^ (rr & 7))) << 4) + (cc & 7) * 2) = __float2half(1.0f);
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+      }
+      ptx::mbar_wait(BAR(B_PREADY + slot), (uint32_t)((m / C::NS) & 1));
+      if (lane == 0) FX_TL(8, i);
+      if (m >= C::NO) ptx::mbar_wait(BAR(B_OFREE + os), (uint32_t)(((m / C::NO) - 1) & 1));
+      ptx::tc_fence_after();
+      const uint32_t vb = smem0 + C::OFF_V + st * C::VSTAGE;
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < kTP / 16; ++ks)          // A = P from tensor memory: 8 columns (16 fp16) per k-step
+          ptx::umma_ts(tmem_base + C::col_o(os), tmem_base + C::col_s(slot) + ks * 8,
+                       ptx::make_sw128_desc(vb + ks * 16 * 128, kKAtom, 1024), idesc_pv, ks > 0);
+        ptx::umma_commit(BAR(B_PVDONE + slot));
+        ptx::umma_commit(BAR(B_VEMPTY + st));
+        FX_TL(9, i);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ============================== softmax groups: 8 warps = 128 rows x 2 column halves ==============================
+    const int sw = warp - 4;                       // 0..15
+    const int g = sw >> 3;                         // softmax group
+    const int c = (sw >> 2) & 1;                   // column half: S columns [40c, 40c + 40)
+    const int qd = sw & 3;                         // TMEM lane quarter (== warp % 4)
+    const int row = (qd << 5) | lane;
+    const uint32_t lane_addr = (uint32_t)(qd << 5) << 16;
+    const float sl2 = p.scale * 1.4426950408889634f;
+    const int pair_bar = 1 + g * 4 + qd;           // named barrier shared by the two warps of a row quarter
+    float* xchg = reinterpret_cast<float*>(smem_gen + C::OFF_XCHG);          // [g][buf][half][128] maxima
+    float* xsum = xchg + 2 * 2 * 2 * 128;                                     // [g][buf][half][128] row sums (!ONES)
+    const uint32_t stg_off = C::OFF_STG + (uint32_t)sw * C::STG_WARP;
+    const int oc0 = c ? C::C0 : 0;                 // first output column of this thread
+    const int ocn = c ? C::C1 : C::C0;             // number of output columns of this thread
+
+    auto warp_arrive = [&](uint32_t bar) {         // one arrive per warp (barrier counts are per warp)
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar);
+    };
+
+    // ---- stat jobs: per-thread partial of the statistic over this thread's 40 columns ----
+    float vmax = -INFINITY;
+    double dsum = 0.0, dsq = 0.0;
+    int cur_li = -1;
+    auto flush = [&]() {
+      if (cur_li < 0) return;
+      double m = vmax, a = dsum, q = dsq;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+      }
+      if (lane == 0 && cur_li < kMaxLocal) {
+        StatPartial sp;
+        sp.vmax = m; sp.sum = a; sp.sumsq = q; sp.pad = 1.0;
+        s_part[sw][cur_li] = sp;
+      }
+      vmax = -INFINITY; dsum = 0.0; dsq = 0.0;
+    };
+
+    for (int i = g; i < ns; i += 2) {              // group g takes the jobs with i % 2 == g
+      const uint2 r = s_jobs[i];
+      const int li = (r.y >> 4) & 3, tile = r.x >> 16;
+      const int slot = i % C::NS;
+      if (li != cur_li) { flush(); cur_li = li; }
+      ptx::mbar_wait(BAR(B_SREADY + slot), (uint32_t)((i / C::NS) & 1));
+      ptx::tc_fence_after();
+      if ((sw & 7) == 0 && lane == 0) FX_TL(4, i);
+      float s[40];
+      tmem_ld40_sync(tmem_base + lane_addr + C::col_s(slot) + c * 40, s);
+      ptx::tc_fence_before();
+      warp_arrive(BAR(B_SFREE + slot));
+      if ((sw & 7) == 0 && lane == 0) FX_TL(5, i);
+      if (tile * kBM + row < p.N) {
+        if (p.stat == PWW_STAT_MAX) {
+          // max(fp16(s)) == fp16(max(s)): rounding is monotonic, so round once at the very end
+          float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 40; j += 2) {
+            if (c * 40 + j < T) m0 = fmaxf(m0, s[j]);
+            if (c * 40 + j + 1 < T) m1 = fmaxf(m1, s[j + 1]);
+          }
+          vmax = fmaxf(vmax, fmaxf(m0, m1));
+        } else {
+          float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 40; j += 2) {
+            // padded columns hold exact zeros (K rows >= T are zero-filled), so they add nothing
+            const __half2 hh = __floats2half2_rn(s[j], s[j + 1]);
+            const float2 f = __half22float2(hh);
+            a0 += f.x; a1 += f.y;
+            q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+          }
+          dsum += (double)(a0 + a1);
+          dsq += (double)(q0 + q1);
+        }
+      }
+    }
+    if (ns > 0) {
+      flush();
+      ptx::named_bar_sync(9, 512);               // all 16 softmax warps have written their partials
+      if (sw == 0) {
+        // publish: one lane per local image reduces the 16 warps in a fixed order, writes the CTA's slot, arrives
+        const int nl = s_nl;
+        if (lane < nl && lane < kMaxLocal) {
+          const int lbv = s_lb[lane];
+          StatPartial sp = s_part[0][lane];
+          for (int w2 = 1; w2 < 16; ++w2) {
+            sp.vmax = fmax(sp.vmax, s_part[w2][lane].vmax);
+            sp.sum += s_part[w2][lane].sum;
+            sp.sumsq += s_part[w2][lane].sumsq;
+          }
+          p.partials[(int64_t)lbv * gridDim.x + blockIdx.x] = sp;
+          __threadfence();
+          atomicAdd(p.counters + lbv, 1u);
+        }
+        if (lane == 0) FX_TL(12, 0);
+        __syncwarp();
+      }
+    }
+
+    // ---- main jobs ----
+    int pend = 0;                                  // 1 = a job of this group has its P.V in flight / finished
+    int pend_slot = 0, pend_os = 0, pend_ph = 0, pend_n0 = 0, pend_b = 0, pend_h = 0, pend_xb = 0;
+    float pend_sum = 0.f;
+    int xb = 0;                                    // exchange buffer parity of this group's next job
+
+    auto epilogue = [&]() {                        // O (fp32, TMEM) -> * 1/rowsum -> fp16 -> staging -> TMA store
+      ptx::mbar_wait(BAR(B_PVDONE + pend_slot), (uint32_t)pend_ph);
+      ptx::tc_fence_after();
+      const uint32_t ta = tmem_base + lane_addr + C::col_o(pend_os);
+#pragma unroll
+      for (int ps = 0; ps < C::EPI_NPASS; ++ps) {
+        float o[41];
+        if constexpr (D == 40) {
+          // columns [oc0, oc0 + 24) (the second half only uses 16 of them) and the row-sum column 40
+          ptx::tmem_ld16_sync(ta + oc0, o);
+          ptx::tmem_ld8_sync(ta + oc0 + 16, o + 16);
+          tmem_ld1_sync(ta + 40, o + 40);
+        } else if constexpr (D == 64) {
+          ptx::tmem_ld32_sync(ta + oc0, o);
+        } else if constexpr (D == 80) {
+          tmem_ld40_sync(ta + oc0, o);
+          tmem_ld1_sync(ta + 80, o + 40);
+        } else {
+          tmem_ld40_sync(ta + oc0 + ps * 40, o);
+        }
+        if (ps == C::EPI_NPASS - 1) {
+          ptx::tc_fence_before();
+          warp_arrive(BAR(B_OFREE + pend_os));     // O is in registers: the next P.V on this accumulator may start
+        }
+        float inv;
+        if constexpr (C::ONES) inv = 1.f / o[40];
+        else inv = 1.f / (pend_sum + xsum[((g * 2 + pend_xb) * 2 + (c ^ 1)) * 128 + row]);
+        // the staging tile is free once the previous store of this warp has been read out (lane 0 owns the groups)
+        if (lane == 0) bulk_wait_group_read0();
+        __syncwarp();
+        const int w8 = (D == 160) ? 5 : (ocn >> 3);      // 16-byte chunks this thread writes
+#pragma unroll
+        for (int ch = 0; ch < C::EPI_W / 8; ++ch) {
+          if (ch < w8) {
+            __align__(16) __half2 pk[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) pk[k] = __floats2half2_rn(o[ch * 8 + 2 * k] * inv, o[ch * 8 + 2 * k + 1] * inv);
+            // staging rows are exactly ocn (or 40) columns wide for the store's box: pitch = box width
+            *reinterpret_cast<uint4*>(smem_gen + stg_off + lane * (((D == 160) ? 40 : ocn) * 2) + ch * 16) =
+                *reinterpret_cast<const uint4*>(pk);
+          }
+        }
+        ptx::fence_proxy_async_smem();             // generic-proxy writes -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0 && pend_n0 < p.N) {          // rows >= N are clipped by the TMA
+          ptx::tma_store_4d(c ? &tmo1 : &tmo0, smem0 + stg_off, oc0 + ps * 40, pend_h, pend_n0, pend_b);
+          ptx::bulk_commit_group();
+        }
+      }
+    };
+
+    for (int i = ns + ((ns & 1) ^ g); i < njobs; i += 2) {          // main jobs with i % 2 == g
+      {
+        const uint2 r = s_jobs[i];
+        const int m = i - ns;
+        const int slot = i % C::NS;
+        const uint32_t ts = tmem_base + lane_addr + C::col_s(slot);
+        ptx::mbar_wait(BAR(B_SREADY + slot), (uint32_t)((i / C::NS) & 1));
+        ptx::tc_fence_after();
+        if ((sw & 7) == 0 && lane == 0) FX_TL(4, i);
+        float s[40];
+        tmem_ld40_sync(ts + c * 40, s);
+        // row max over this thread's columns (padded keys excluded), then over the row via the partner thread
+        if constexpr (TT == 77) {
+          if (c) { s[37] = -INFINITY; s[38] = -INFINITY; s[39] = -INFINITY; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 40; ++j)
+            if (c * 40 + j >= T) s[j] = -INFINITY;
+        }
+        float m0 = s[0], m1 = s[1], m2 = s[2], m3 = s[3];
+#pragma unroll
+        for (int j = 4; j < 40; j += 4) {
+          m0 = fmaxf(m0, s[j]); m1 = fmaxf(m1, s[j + 1]); m2 = fmaxf(m2, s[j + 2]); m3 = fmaxf(m3, s[j + 3]);
+        }
+        float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        float* xm = xchg + ((g * 2 + xb) * 2) * 128;
+        xm[c * 128 + row] = mx;
+        ptx::named_bar_sync(pair_bar, 64);
+        mx = fmaxf(mx, xm[(c ^ 1) * 128 + row]);
+        const float nm = -mx * sl2;
+        // p_j = 2^(s_j*sl2 - mx*sl2), UNNORMALISED, packed to fp16; O is scaled by 1/rowsum in the epilogue (fp32)
+        float a0 = 0.f, a1 = 0.f;
+        uint32_t pk[20];
+#pragma unroll
+        for (int j = 0; j < 40; j += 2) {
+          const float e0 = ptx::ex2(fmaf(s[j], sl2, nm)), e1 = ptx::ex2(fmaf(s[j + 1], sl2, nm));
+          const __half2 h = __floats2half2_rn(e0, e1);
+          pk[j / 2] = *reinterpret_cast<const uint32_t*>(&h);
+          if constexpr (!C::ONES) {
+            const float2 f = __half22float2(h);       // sum exactly what the UMMA will multiply
+            a0 += f.x; a1 += f.y;
+          }
+        }
+        if constexpr (!C::ONES) xsum[((g * 2 + xb) * 2 + c) * 128 + row] = a0 + a1;
+        // P (packed fp16) over the S columns it came from: this half owns P columns [20c, 20c + 20)
+        ptx::tmem_st16_u32(ts + c * 20, pk);
+        tmem_st4_u32(ts + c * 20 + 16, pk + 16);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        warp_arrive(BAR(B_PREADY + slot));
+        if ((sw & 7) == 0 && lane == 0) FX_TL(5, i);
+        if (pend) epilogue();                      // overlaps with this job's P.V
+        if ((sw & 7) == 0 && lane == 0) FX_TL(6, i);
+        pend = 1;
+        pend_slot = slot;
+        pend_os = i % C::NO;
+        pend_ph = (m / C::NS) & 1;
+        pend_n0 = (int)(r.x >> 16) * kBM + (qd << 5);
+        pend_b = r.x & 0xff;
+        pend_h = (r.x >> 8) & 0xff;
+        pend_xb = xb;
+        pend_sum = a0 + a1;
+        xb ^= 1;
+      }
+    }
+    if (pend) {
+      if constexpr (!C::ONES) ptx::named_bar_sync(pair_bar, 64);   // the partner's row sum of the last job is written
+      epilogue();
+    }
+    if (lane == 0) ptx::bulk_wait_group0();        // the staging tile must outlive the last store
+    if ((sw & 7) == 0 && lane == 0) FX_TL(14, g);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) FX_TL(15, 0);
+  if (warp == 1) ptx::tmem_dealloc<512>(tmem_base);
+  // the last CTA to leave resets the arrival counters for the next launch (every waiter has passed its barrier)
+  if (threadIdx.x == 0 && nb > 0) {
+    __threadfence();
+    const unsigned prev = atomicAdd(p.counters + kMaxBatch, 1u);
+    if (prev == gridDim.x - 1u) {
+      for (int b = 0; b < kMaxBatch + 1; ++b) p.counters[b] = 0u;
+      __threadfence();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+// Q [B, N, H*D] fp16 viewed as (column, row, image): boxes of [64 columns x 128 rows x 1] = whole 128-byte lines,
+// 128-byte swizzle.  Columns beyond H*D and rows beyond N are zero-filled.
+inline bool make_tmap_qfull(CUtensorMap* m, const void* base, int C, int N, int B, int64_t row_stride, int64_t batch_stride) {
+  tc::EncodeTiledFn fn = tc::encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)N, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)row_stride * 2, (cuuint64_t)(batch_stride > 0 ? batch_stride : (int64_t)N * row_stride) * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)kBM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    snprintf(tc::tc_error_buf(), 256, "cuTensorMapEncodeTiled(q rows) failed (CUresult %d): base %p C %d N %d B %d strides %lld %lld",
+             (int)r, base, C, N, B, (long long)row_stride, (long long)batch_stride);
+  return r == CUDA_SUCCESS;
+}
+
+// A launch fits when every CTA's unit range touches at most kMaxLocal biased images and holds at most kMaxUnits units
+// (job table in shared memory); the C ABI halves the images per launch until it does.
+inline bool fused2_fits(int B, int hg, int tiles, int grid) {
+  const long long units = (long long)B * hg * tiles;
+  return fused_range_ok(B, hg, tiles, grid) && (units + grid - 1) / grid + 1 <= kMaxUnits;
+}
+
+template <int D>
+cudaError_t launch_fused2(const XattnParams& x, const void* mpack, int64_t mpack_bs, int Bw, const int8_t* cidx,
+                          cudaStream_t s) {
+  using C = Cfg2<D>;
+  CUtensorMap tq, tk, tv, tm, to0, to1;
+  const int kB = x.k_bs > 0 ? x.B : 1;
+  if (!make_tmap_qfull(&tq, x.q, x.H * D, x.N, x.B, x.q_rs, x.q_bs) ||
+      !tc::make_tmap(&tk, x.k, D, x.H, x.T, kB, x.k_rs, x.k_bs, kTP) ||
+      !tc::make_tmap(&tv, x.v, D, x.H, x.T, kB, x.k_rs, x.k_bs, kTP))
+    return cudaErrorInvalidValue;
+  if (mpack != nullptr) {
+    if (!make_tmap_mpack(&tm, mpack, x.N, Bw, mpack_bs)) return cudaErrorInvalidValue;
+  } else {
+    tm = tq;                                       // never dereferenced: no image is biased
+  }
+  if (!tc::make_tmap_out(&to0, x.out, D, x.H, x.N, x.B, x.o_rs, x.o_bs, 32, C::C0, false) ||
+      !tc::make_tmap_out(&to1, x.out, D, x.H, x.N, x.B, x.o_rs, x.o_bs, 32, C::C1, false))
+    return cudaErrorInvalidValue;
+  FxParams fp;
+  fp.x = x;
+  fp.cidx = cidx;
+  fp.tiles = ceil_div(x.N, kBM);
+  fp.hg = ceil_div(x.H, C::G);
+  fp.units = x.B * fp.tiles * fp.hg;
+  fp.k_batched = x.k_bs > 0 ? 1 : 0;
+  fp.grid = fused_grid(fp.units);
+  fp.timeline = debug_timeline();
+  fp.tl_cta = debug_timeline_cta();
+  fp.jobs_dump = debug_jobs_dump();
+  if (!fused2_fits(x.B, fp.hg, fp.tiles, fp.grid)) return cudaErrorInvalidConfiguration;
+  static bool attr_set[tc::kMaxDevices] = {false};
+  if (!attr_set[tc::cur_device()]) {
+    cudaError_t e = cudaFuncSetAttribute(xattn_fused2_kernel<D, 77>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(xattn_fused2_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set[tc::cur_device()] = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(fp.grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::SMEM;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;     // all CTAs co-resident: the in-kernel grid barrier cannot deadlock
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (x.T == 77) return cudaLaunchKernelEx(&cfg, xattn_fused2_kernel<D, 77>, tq, tk, tv, tm, to0, to1, fp);
+  return cudaLaunchKernelEx(&cfg, xattn_fused2_kernel<D, 0>, tq, tk, tv, tm, to0, to1, fp);
+}
+
+// Host replay of the job lists (test infrastructure): out[job] = {cta, i, kind, m, b, h, tile, biased, li, gi, up, ul,
+// first, last} for every job of every CTA; returns the number of jobs written.
+inline int fused2_schedule_host(int B, int H, int G, int tiles, int grid, const int* wmap_index, int* out, int max_jobs) {
+  if (B <= 0 || B > kMaxBatch || H <= 0 || G <= 0 || tiles <= 0 || grid <= 0) return -1;
+  int img[kMaxBatch];
+  int nb = 0;
+  for (int b = 0; b < B; ++b) if (wmap_index[b] >= 0) img[nb++] = b;
+  int nu = 0;
+  for (int b = 0; b < B; ++b) if (wmap_index[b] < 0) img[nb + nu++] = b;
+  const int hg = (H + G - 1) / G;
+  const int units = B * hg * tiles;
+  int row = 0;
+  for (int cta = 0; cta < grid; ++cta) {
+    int u0, u1;
+    fx_range(cta, grid, units, u0, u1);
+    Fx2Jobs jobs(u0, u1 - u0, B, H, G, tiles, nb, img);
+    Fx2Job jb;
+    while (jobs.next(jb)) {
+      if (row >= max_jobs) return -2;
+      int* o = out + 14 * (row++);
+      o[0] = cta; o[1] = jb.i; o[2] = jb.kind; o[3] = jb.m; o[4] = jb.b; o[5] = jb.h; o[6] = jb.tile; o[7] = jb.biased;
+      o[8] = jb.li; o[9] = jb.gi; o[10] = jb.up; o[11] = jb.ul; o[12] = jb.first; o[13] = jb.last;
+    }
+  }
+  return row;
+}
+
+}  // namespace fx2
+}  // namespace pww

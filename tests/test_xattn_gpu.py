@@ -326,3 +326,54 @@ def test_pack_cache_is_not_fooled_by_address_reuse():
     ref_b, _ = _oracle(q, k, v, H, D ** -0.5, w2, g, "max", emulate=False)
     assert (a - ref_a).abs().max().item() <= 2e-3 * ref_a.abs().max().item()
     assert (b - ref_b).abs().max().item() <= 2e-3 * ref_b.abs().max().item()
+
+
+@pytest.mark.parametrize("B,N,H,grid,idx", [
+    (2, 4096, 8, 0, [0, -1]), (2, 4096, 8, 0, [-1, 0]), (16, 4096, 8, 0, [v for i in range(8) for v in (i, -1)]),
+    (16, 2048, 8, 0, list(range(8)) + [-1] * 8), (3, 1024, 5, 0, [0, 1, -1]), (4, 640, 3, 20, [-1, -1, -1, 0]),
+    (5, 384, 10, 7, [0, 1, 2, 3, 4]), (4, 1024, 8, 8, [0, -1, 1, -1]), (2, 1024, 8, 3, [0, -1]), (5, 333, 3, 4, [0, -1, 1, -1, 2]),
+    (1, 100, 1, 0, [0])])
+def test_grouped_head_job_table_built_on_the_device_equals_the_host_replay(B, N, H, grid, idx):
+    """The grouped-head kernel (head dim 40) builds every CTA's job table in shared memory with ballots and warp scans;
+    the library's host replay walks the same lists sequentially (tests/test_fused2_schedule.py checks ITS invariants).
+    Dump the device tables and compare them job by job."""
+    import ctypes
+    L = _native.lib()
+    D, T, G = 40, 77, 4
+    q, k, v, w = _inputs(B, N, H, D, T, seed=B + N + H)
+    nbw = max(idx) + 1
+    tiles = (N + 127) // 128
+    hg = (H + G - 1) // G
+    units = B * hg * tiles
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    g = min(units, sms if grid == 0 else min(grid, sms))
+    dump = torch.zeros(g * (2 + 1024), dtype=torch.int32, device="cuda")
+    L.pww_debug_set_fused_jobs_dump.argtypes = [ctypes.c_void_p]
+    _set_fused_grid(grid)
+    L.pww_debug_set_fused_jobs_dump(dump.data_ptr())
+    try:
+        _run(q, k, v, H, D ** -0.5, w[:nbw].contiguous(), 0.5, "max", torch.tensor(idx, dtype=torch.int32))
+    finally:
+        L.pww_debug_set_fused_jobs_dump(None)
+        _set_fused_grid(0)
+    d = dump.cpu().numpy().astype(np.int64).reshape(g, 2 + 1024)
+    L.pww_debug_fused2_schedule.restype = ctypes.c_int
+    L.pww_debug_fused2_schedule.argtypes = [ctypes.c_int] * 5 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    widx = np.asarray(idx, dtype=np.int32)
+    cap = 2 * B * H * tiles + 8
+    out = np.full((cap, 14), -7, dtype=np.int32)
+    n = L.pww_debug_fused2_schedule(B, H, G, tiles, g, widx.ctypes.data, out.ctypes.data, cap)
+    assert n > 0
+    host = out[:n]
+    for cta in range(g):
+        rows = host[host[:, 0] == cta]
+        njobs, ns = int(d[cta, 0]), int(d[cta, 1])
+        assert njobs == len(rows) and ns == int((rows[:, 2] == 0).sum())
+        for r in rows:
+            i = int(r[1])
+            x, y = int(d[cta, 2 + 2 * i]) & 0xFFFFFFFF, int(d[cta, 3 + 2 * i]) & 0xFFFFFFFF
+            assert (x & 0xFF, (x >> 8) & 0xFF, x >> 16) == (r[4], r[5], r[6]), (cta, i)
+            assert (y & 1, (y >> 1) & 1, (y >> 2) & 1, (y >> 3) & 1) == (r[2], r[7], r[12], r[13]), (cta, i)
+            assert ((y >> 8) & 0xFF) == r[11]
+            if r[7]:
+                assert ((y >> 4) & 3) == r[8]
