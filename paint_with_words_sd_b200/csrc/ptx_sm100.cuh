@@ -64,6 +64,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Wait for two / three phases at once: the first probes are issued back to back so their latencies overlap (a control
+// warp that waits for "operand landed" and "accumulator free" pays one round trip, not one per barrier).
+__device__ __forceinline__ void mbar_wait2(uint32_t bar_a, uint32_t par_a, uint32_t bar_b, uint32_t par_b) {
+  const bool a = mbar_test(bar_a, par_a), b = mbar_test(bar_b, par_b);
+  if (!a) mbar_wait(bar_a, par_a);
+  if (!b) mbar_wait(bar_b, par_b);
+}
+__device__ __forceinline__ void mbar_wait3(uint32_t bar_a, uint32_t par_a, uint32_t bar_b, uint32_t par_b, uint32_t bar_c,
+                                           uint32_t par_c) {
+  const bool a = mbar_test(bar_a, par_a), b = mbar_test(bar_b, par_b), c = mbar_test(bar_c, par_c);
+  if (!a) mbar_wait(bar_a, par_a);
+  if (!b) mbar_wait(bar_b, par_b);
+  if (!c) mbar_wait(bar_c, par_c);
+}
+
 // ---------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

@@ -185,7 +185,7 @@ int pww_xattn_fused_f16(const void* q, const void* k, const void* v, void* out, 
   p.o_bs = o_batch_stride; p.o_rs = o_row_stride;
   p.g_sigma = g_sigma; p.scale = scale; p.stat = stat;
   p.counters = (unsigned int*)workspace;
-  p.partials = workspace ? (pww::StatPartial*)((char*)workspace + 256) : nullptr;
+  p.partials = workspace ? (pww::StatPartial*)((char*)workspace + 512) : nullptr;   // header: counters @0, per-image maxima @256
   cudaStream_t s = (cudaStream_t)stream;
   // image b is biased iff it has a packed map: with mpack == NULL every index is -1 (the kernel reads wmap_index)
   int chunk = pww::fx::kMaxBatch;                                  // images per launch

@@ -96,7 +96,7 @@ struct FxParams {
   int hg;                   // head groups per row tile (grouped-head kernel, xattn_fused2.cuh)
   unsigned* jobs_dump;      // debug only: [grid][2 + 2 * 512] = njobs, nstat, job table of every CTA (grouped-head kernel)
 };
-constexpr int kFxTlTags = 16, kFxTlIts = 64;
+constexpr int kFxTlTags = 24, kFxTlIts = 64;
 #define FX_TL(tag, it)                                                                                     \
   do {                                                                                                     \
     if (fp.timeline != nullptr && (int)blockIdx.x == fp.tl_cta && (it) >= 0 && (it) < kFxTlIts)           \
@@ -896,7 +896,7 @@ inline bool fused_range_ok(int B, int H, int tiles, int grid) {
   return per_cta <= (long long)(kMaxLocal - 1) * tiles * H;
 }
 inline size_t fused_workspace_bytes() {
-  return 256 + (size_t)kMaxBatch * 2048 * sizeof(StatPartial) / 8;   // counters + [32][256] partial slots
+  return 512 + (size_t)kMaxBatch * 2048 * sizeof(StatPartial) / 8;   // counters | per-image maxima | [32][256] partial slots
 }
 
 template <int D>

@@ -13,7 +13,12 @@
 //                 both sides), and the neighbouring heads' Q columns inside the blocks meet zeros.
 // A CTA whose whole unit range fits the Q ring (<= 2 units: the cond + uncond launch of the denoising loop puts at most
 // one unit on a CTA) keeps its Q tiles resident: the statistic pass and the softmax pass read Q from HBM once.
-// K and V tiles of a head ([80 x 64] fp16 atoms) travel in their own rings, per job, from L2.
+// K and V tiles of a head ([80 x 64] fp16 atoms) do NOT use the TMA: a [77 x 80 B] box costs the engine ~930 cycles even from
+// L2 (it is row-rate bound, ~12 cycles per short misaligned row; timeline in profiles/r02_fused2_uniform_timeline_*), more
+// than the 616 MUFU cycles of the job's softmax.  Two loader warps copy them straight into
+// the swizzled atoms (K shifted by one 16-byte chunk for odd heads, V with its ones column and zero padding written once
+// per ring stage) as 16-byte cp.async copies that arrive on the stage's mbarrier -- no staging registers, a whole ring of
+// tiles in flight.
 #pragma once
 #include "ptx_sm100.cuh"
 #include "pww_common.cuh"
@@ -144,6 +149,30 @@ constexpr int kMaxUnits = 64;        // units per CTA (host-checked: the C ABI s
 constexpr int kMaxJobs = 512;        // kMaxUnits * G heads * 2 passes
 constexpr uint32_t JF_MAIN = 1u, JF_BIASED = 2u, JF_FIRST = 4u, JF_LAST = 8u;   // | li << 4 (2 bits) | ul << 8 (8 bits)
 
+// Order-preserving map float -> unsigned (0 is below every real number: a zero-filled workspace reads as -infinity).
+__device__ __forceinline__ unsigned f32_key(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_f32(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+// 16-byte asynchronous copy global -> shared (LDGSTS): no staging registers, many tiles in flight.  src_bytes = 0 writes zeros.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// one arrival on `bar` once every cp.async this thread has issued so far has landed (the count is part of the barrier's
+// expected arrivals: 32 lanes -> init 32)
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+// Per-image synchronisation word of the grid barrier (workspace + 256 + 8 b): low half = order-preserving key of the running
+// maximum (atomic max), high half = number of CTAs that have published.  One acquire load returns both.
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ bool elect_one() {     // true on exactly one lane of a converged warp
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -152,12 +181,12 @@ __device__ __forceinline__ bool elect_one() {     // true on exactly one lane of
 
 template <int D, int TT>
 __global__ void __launch_bounds__(kThreads, 1)
-xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
-                    const __grid_constant__ CUtensorMap tmv, const __grid_constant__ CUtensorMap tmm,
+xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmm,
                     const __grid_constant__ CUtensorMap tmo0, const __grid_constant__ CUtensorMap tmo1,
                     const FxParams fp) {
   using C = Cfg2<D>;
   const XattnParams& p = fp.x;
+  if (threadIdx.x == 0) FX_TL(21, 0);
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   unsigned char* smem_gen = smem_raw + (smem0 - ptx::smem_u32(smem_raw));
@@ -182,7 +211,65 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   __shared__ float s_coef[kMaxLocal];             // g(sigma) * statistic of the CTA's local biased images
   __shared__ StatPartial s_part[16][kMaxLocal];   // [softmax warp][local biased image]
   __shared__ uint2 s_jobs[kMaxJobs];
+  __shared__ int s_img0[kMaxBatch], s_widx0[kMaxBatch], s_pre;   // producer warp's own copy of the partition; early Q loads
 
+  if (warp == 0) {
+    // ---- early Q: the first unit passes' tiles are requested BEFORE the prologue's block-wide sync, so the ~2 us of cold
+    //      HBM latency overlap TMEM allocation and the job-table build.  The warp partitions the images itself (same
+    //      ballots as warp 2), initialises the Q barriers and issues the loads of unit passes 0 .. s_pre - 1. ----
+    const int b = lane;
+    const int wi = (b < p.B && p.wmap != nullptr) ? (p.wmap_index ? p.wmap_index[b] : b) : -1;
+    const bool valid = b < p.B, bi = valid && wi >= 0;
+    const unsigned mbk = __ballot_sync(0xffffffffu, bi), muk = __ballot_sync(0xffffffffu, valid && !bi);
+    const unsigned ltk = (1u << lane) - 1u;
+    const int nb0 = __popc(mbk);
+    if (bi) s_img0[__popc(mbk & ltk)] = b;
+    else if (valid) s_img0[nb0 + __popc(muk & ltk)] = b;
+    if (valid) s_widx0[b] = wi;
+    __syncwarp();
+    if (lane == 0) {
+      ptx::prefetch_tmap(&tmq);
+      ptx::prefetch_tmap(&tmm);
+      for (int s = 0; s < C::NQ; ++s) {
+        ptx::mbar_init(BAR(B_QFULL + s), 1);
+        ptx::mbar_init(BAR(B_QEMPTY + s), 1);
+      }
+      ptx::fence_barrier_init();
+      // unit passes in job order: biased units (statistic pass; in resident mode the one load serves both passes), then
+      // unbiased units.  Resident: unit ul -> stage ul.  Ring: pass up -> stage up % NQ, only the first NQ go out here.
+      int pre = 0;
+      FxWalk w(u0, p.B, HG, fp.tiles, nb0, s_img0);
+      if (resident) {
+        for (int ul = 0; ul < n_it; ++ul, w.next()) {
+          const FxUnit u = w.get();
+          const uint32_t qb = smem0 + ul * C::QSTAGE;
+          ptx::mbar_arrive_expect_tx(BAR(B_QFULL + ul), C::QBYTES + (u.biased ? kMAtom : 0u));
+          const int atom0 = (u.h * C::G * D) / 64;
+          for (int a = 0; a < C::NAQ; ++a)
+            tma_load_3d(qb + a * kQAtom, &tmq, BAR(B_QFULL + ul), (atom0 + a) * 64, u.tile * kBM, u.b);
+          if (u.biased) tma_load_3d(qb + C::QBYTES, &tmm, BAR(B_QFULL + ul), 0, u.tile * kBM, s_widx0[u.b]);
+        }
+        pre = n_it;
+      } else {
+        for (int pass = 0; pass < 2 && pre < C::NQ; ++pass) {        // pass 0: biased units, pass 1: unbiased units
+          if (pass == 0 && nb0 == 0) continue;
+          FxWalk w2 = w;
+          for (int it = 0; it < n_it && pre < C::NQ; ++it, w2.next()) {
+            const FxUnit u = w2.get();
+            if ((u.biased != 0) != (pass == 0)) continue;
+            const uint32_t qb = smem0 + pre * C::QSTAGE;
+            ptx::mbar_arrive_expect_tx(BAR(B_QFULL + pre), C::QBYTES);    // statistic / unbiased passes read no map
+            const int atom0 = (u.h * C::G * D) / 64;
+            for (int a = 0; a < C::NAQ; ++a)
+              tma_load_3d(qb + a * kQAtom, &tmq, BAR(B_QFULL + pre), (atom0 + a) * 64, u.tile * kBM, u.b);
+            ++pre;
+          }
+        }
+      }
+      s_pre = pre;
+    }
+    __syncwarp();
+  }
   if (warp == 2) {
     // ---- stable partition of the images by "has a weight map" ----
     {
@@ -253,27 +340,37 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       }
     }
     if (lane == 0) { s_njobs = 2 * ns + nuj; s_nstat = ns; s_nl = c_li + 1; }
+    if (lane == 0) FX_TL(22, 0);
   }
   for (int i = threadIdx.x; i < 16 * kMaxLocal; i += kThreads) {
     StatPartial sp;
     sp.vmax = -INFINITY; sp.sum = 0.0; sp.sumsq = 0.0; sp.pad = 0.0;
     s_part[i / kMaxLocal][i % kMaxLocal] = sp;
   }
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tmq);
-    ptx::prefetch_tmap(&tmk);
-    ptx::prefetch_tmap(&tmv);
-    ptx::prefetch_tmap(&tmm);
+  // K / V ring stages, once: zero rows T..79 (the per-job copies never touch them); V chunk column 5 = [1.0, 0 x 7] for real
+  // tokens -- the spare column that makes accumulator column D of the P.V UMMA the row sum -- and zero for padded ones.
+  for (int idx = threadIdx.x; idx < C::NK * (kTP - T) * 6; idx += kThreads) {
+    const int stz = idx / ((kTP - T) * 6), rem = idx - stz * ((kTP - T) * 6);
+    const int t = T + rem / 6, ch = rem % 6;
+    *reinterpret_cast<uint4*>(smem_gen + C::OFF_K + stz * C::KSTAGE + t * 128 + ((ch ^ (t & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+  }
+  for (int idx = threadIdx.x; idx < C::NV * kTP; idx += kThreads) {
+    const int stz = idx / kTP, t = idx - stz * kTP;
+    unsigned char* vrow = smem_gen + C::OFF_V + stz * C::VSTAGE + t * 128;
+    if (t >= T) {
+#pragma unroll
+      for (int ch = 0; ch < 5; ++ch) *reinterpret_cast<uint4*>(vrow + ((ch ^ (t & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+    }
+    *reinterpret_cast<uint4*>(vrow + ((5 ^ (t & 7)) << 4)) = make_uint4(t < T ? 0x00003C00u : 0u, 0, 0, 0);
+  }
+  ptx::fence_proxy_async_smem();                   // generic-proxy writes above -> visible to the UMMAs (async proxy)
+  if (warp == 3 && lane == 0) {
     ptx::prefetch_tmap(&tmo0);
     ptx::prefetch_tmap(&tmo1);
-    for (int s = 0; s < C::NQ; ++s) {
-      ptx::mbar_init(BAR(B_QFULL + s), 1);
-      ptx::mbar_init(BAR(B_QEMPTY + s), 1);
-    }
     for (int s = 0; s < 3; ++s) {
-      ptx::mbar_init(BAR(B_KFULL + s), 1);
+      ptx::mbar_init(BAR(B_KFULL + s), 32);      // one cp.async arrival per lane of the loader warp
       ptx::mbar_init(BAR(B_KEMPTY + s), 1);
-      ptx::mbar_init(BAR(B_VFULL + s), 1);
+      ptx::mbar_init(BAR(B_VFULL + s), 32);
       ptx::mbar_init(BAR(B_VEMPTY + s), 1);
     }
     for (int s = 0; s < 4; ++s) {
@@ -287,7 +384,10 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     ptx::mbar_init(BAR(B_COEF + 1), 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc<512>(BAR(B_TMEMPTR));
+  if (warp == 1) {
+    ptx::tmem_alloc<512>(BAR(B_TMEMPTR));
+    if (lane == 0) FX_TL(23, 0);
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -307,8 +407,28 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     for (int b = threadIdx.x; b < p.B; b += kThreads)
       if (s_widx[b] < 0) p.stats_out[b] = 0.f;
 
+  // One head's K or V rows ([T x D] fp16 = 5 chunks of 16 bytes per row) into a swizzled [80 x 128 B] atom with 16-byte
+  // asynchronous copies, data chunk `ch` landing in chunk column ch + shift; chunk column `zc` (< 0: none) is zero-filled.
+  auto copy_kv = [&](uint32_t tile, const __half* base, unsigned x, int shift, int zc, uint32_t bar) {
+    const int b = x & 0xff, h = (x >> 8) & 0xff;
+    const __half* src = base + (fp.k_batched ? (int64_t)b * p.k_bs : 0) + h * D;
+#pragma unroll
+    for (int jj = 0; jj < (kTP + 31) / 32; ++jj) {       // a lane owns whole rows: one address computation per row
+      const int t = lane + 32 * jj;
+      if (t < T) {
+        const uint4* srow = reinterpret_cast<const uint4*>(src + (int64_t)t * p.k_rs);
+        const uint32_t drow = tile + t * 128;
+        const int x7 = t & 7;
+#pragma unroll
+        for (int ch = 0; ch < 5; ++ch) cp_async16(drow + (((ch + shift) ^ x7) << 4), srow + ch, 16u);
+        if (zc >= 0) cp_async16(drow + ((zc ^ x7) << 4), srow, 0u);
+      }
+    }
+    cp_async_arrive(bar);
+  };
+
   if (warp == 0) {
-    // ============================== TMA producer: Q (+ packed map) per unit pass, K per job ==============================
+    // ============================== producer: Q (+ packed map) by TMA per unit pass, K tiles by loads per job ==============================
     auto load_q = [&](int qst, int b, int tile, int hgi, bool with_map) {     // elected lane only
       const uint32_t qb = smem0 + qst * C::QSTAGE;
       ptx::mbar_arrive_expect_tx(BAR(B_QFULL + qst), C::QBYTES + (with_map ? kMAtom : 0u));
@@ -318,28 +438,14 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         tma_load_3d(qb + a * kQAtom, &tmq, BAR(B_QFULL + qst), (atom0 + a) * 64, tile * kBM, b);
       if (with_map) tma_load_3d(qb + C::QBYTES, &tmm, BAR(B_QFULL + qst), 0, tile * kBM, s_widx[b]);
     };
-    if (resident) {                                // every unit of the range owns a stage: all loads go out now
-      unsigned loaded = 0;
-      for (int i = 0; i < njobs; ++i) {
-        const uint2 r = s_jobs[i];
-        const int ul = (r.y >> 8) & 0xff;
-        if ((r.y & JF_FIRST) && !((loaded >> ul) & 1u)) {
-          loaded |= 1u << ul;
-          if (elect_one()) {
-            load_q(ul, r.x & 0xff, r.x >> 16, (int)((r.x >> 8) & 0xff) / C::G, (r.y & JF_BIASED) != 0);
-            FX_TL(0, i);
-          }
-          __syncwarp();
-        }
-      }
-    }
+    const int pre = s_pre;                         // unit passes whose Q tile was requested in the prologue
     int up = -1;
     for (int i = 0; i < njobs; ++i) {
       const uint2 r = s_jobs[i];
       const int b = r.x & 0xff, h = (r.x >> 8) & 0xff, tile = r.x >> 16;
       if (r.y & JF_FIRST) {
         ++up;
-        if (!resident) {                             // ring mode: one load per unit pass
+        if (!resident && up >= pre) {                // ring mode: one load per unit pass
           const int qst = up % C::NQ;
           ptx::mbar_wait(BAR(B_QEMPTY + qst), (uint32_t)(((up / C::NQ) & 1) ^ 1));
           if (elect_one()) {
@@ -350,34 +456,42 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
           __syncwarp();
         }
       }
+      // ---- K'_h tile: the head's rows into the swizzled atom, shifted by one 16-byte chunk for odd heads (the head starts
+      //      8 columns into its first 16-column block); the chunk column the shift leaves free is zeroed ----
       const int st = i % C::NK;
       ptx::mbar_wait(BAR(B_KEMPTY + st), (uint32_t)(((i / C::NK) & 1) ^ 1));
-      if (elect_one()) {
-        ptx::mbar_arrive_expect_tx(BAR(B_KFULL + st), C::KSTAGE);
-        // K'_h: the head's 40 columns placed 0 or 8 columns into the tile (see the header); the rest is TMA zero fill
-        ptx::tma_load_4d(smem0 + C::OFF_K + st * C::KSTAGE, &tmk, BAR(B_KFULL + st), -((h * D) % 16), h, 0,
-                         fp.k_batched ? b : 0);
-      }
-      __syncwarp();
+      const int sh = ((h * D) % 16) ? 1 : 0;
+      copy_kv(smem0 + C::OFF_K + st * C::KSTAGE, p.k, r.x, sh, sh ? 0 : 5, BAR(B_KFULL + st));
     }
   } else if (warp == 2) {
-    // ============================== TMA producer: V tiles of the main jobs ==============================
+    // ============================== loader: V tiles of the main jobs ==============================
     for (int i = ns; i < njobs; ++i) {
-      const uint2 r = s_jobs[i];
       const int m = i - ns, st = m % C::NV;
       ptx::mbar_wait(BAR(B_VEMPTY + st), (uint32_t)(((m / C::NV) & 1) ^ 1));
-      if (elect_one()) {
-        ptx::mbar_arrive_expect_tx(BAR(B_VFULL + st), C::VSTAGE);
-        ptx::tma_load_4d(smem0 + C::OFF_V + st * C::VSTAGE, &tmv, BAR(B_VFULL + st), 0, (r.x >> 8) & 0xff, 0,
-                         fp.k_batched ? (int)(r.x & 0xff) : 0);
-      }
-      __syncwarp();
+      copy_kv(smem0 + C::OFF_V + st * C::VSTAGE, p.v, s_jobs[i].x, 0, -1, BAR(B_VFULL + st));
     }
   } else if (warp == 1) {
     // ============================== UMMA issuer: S of every job (+ grid barrier and the bias operand) ==============================
     constexpr uint32_t idesc_qk = ptx::make_idesc_f16(128, kTP, false, false);
     bool stats_ready = false;
     int cur_li = -1, up = -1;
+    // how many CTAs publish a partial for each of my local biased images: counted now, off the critical path
+    int expect_l[kMaxLocal];
+    {
+      const int nl = s_nl, G = (int)gridDim.x;
+#pragma unroll
+      for (int l = 0; l < kMaxLocal; ++l) {
+        int e = 0;
+        if (l < nl) {
+          const int pos = s_lp[l];
+          for (int c = lane; c < G; c += 32) e += fx_cta_has_image(c, G, fp.units, pos, HG, fp.tiles, np) ? 1 : 0;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+        }
+        expect_l[l] = e;
+      }
+    }
+    const unsigned long long* sync_words = reinterpret_cast<const unsigned long long*>(p.counters + 64);
     for (int i = 0; i < njobs; ++i) {
       const uint2 r = s_jobs[i];
       const int b = r.x & 0xff, h = (r.x >> 8) & 0xff;
@@ -390,42 +504,40 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
           const int nl = s_nl;
           const int G = (int)gridDim.x;
           if (lane == 0) FX_TL(10, 0);
-          for (int l = 0; l < nl && l < kMaxLocal; ++l) {
-            const int bl = s_lb[l], pos = s_lp[l];
-            int expect = 0, first_c = 1 << 30;
-            for (int c = lane; c < G; c += 32)
-              if (fx_cta_has_image(c, G, fp.units, pos, HG, fp.tiles, np)) { ++expect; if (c < first_c) first_c = c; }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              expect += __shfl_xor_sync(0xffffffffu, expect, o);
-              first_c = min(first_c, __shfl_xor_sync(0xffffffffu, first_c, o));
-            }
+          for (int l = 0; l < kMaxLocal; ++l) {
+            if (l >= nl) break;
+            const int bl = s_lb[l], pos = s_lp[l];
+            const unsigned expect = (unsigned)expect_l[l];
+            unsigned long long word = 0;
             if (lane == 0) {
               const long long t0 = clock64();
-              while (ld_acquire_gpu(p.counters + bl) < (unsigned)expect) {
-                __nanosleep(32);
+              while ((unsigned)((word = ld_acquire_gpu_u64(sync_words + bl)) >> 32) < expect) {
                 if (clock64() - t0 > 20000000000LL) {
-                  printf("pww: grid barrier timeout block %d image %d have %u want %d\n", blockIdx.x, bl,
-                         ld_acquire_gpu(p.counters + bl), expect);
+                  printf("pww: grid barrier timeout block %d image %d have %u want %u\n", blockIdx.x, bl,
+                         (unsigned)(word >> 32), expect);
                   __trap();
                 }
               }
             }
             __syncwarp();
-            (void)ld_acquire_gpu(p.counters + bl);                 // every lane orders its partial loads behind the counter
             double m = -INFINITY, a = 0.0, q = 0.0;
-            for (int c = lane; c < G; c += 32)
-              if (fx_cta_has_image(c, G, fp.units, pos, HG, fp.tiles, np)) {
-                const StatPartial* pp = p.partials + (int64_t)bl * G + c;
-                m = fmax(m, __ldcg(&pp->vmax));
-                a += __ldcg(&pp->sum);
-                q += __ldcg(&pp->sumsq);
-              }
+            if (p.stat == PWW_STAT_MAX) {
+              // the maximum is order independent: every publisher folded its partial into the word with an atomic max
+              m = (double)key_f32((unsigned)word);
+            } else {
+              (void)ld_acquire_gpu_u64(sync_words + bl);           // every lane orders its partial loads behind the count
+              for (int c = lane; c < G; c += 32)
+                if (fx_cta_has_image(c, G, fp.units, pos, HG, fp.tiles, np)) {
+                  const StatPartial* pp = p.partials + (int64_t)bl * G + c;
+                  a += __ldcg(&pp->sum);
+                  q += __ldcg(&pp->sumsq);
+                }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-              a += __shfl_xor_sync(0xffffffffu, a, o);
-              q += __shfl_xor_sync(0xffffffffu, q, o);
+              for (int o = 16; o > 0; o >>= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, o);
+                q += __shfl_xor_sync(0xffffffffu, q, o);
+              }
             }
             if (lane == 0) {
               const double cnt = (double)p.H * (double)p.N * (double)p.T;
@@ -438,7 +550,7 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
               }
               const float st16 = round_to_f16((float)rr);         // qk.max() / qk.std() return fp16 in the reference
               s_coef[l] = __ldg(p.g_sigma) * st16;
-              if (first_c == (int)blockIdx.x && p.stats_out != nullptr) p.stats_out[bl] = st16;
+              if (p.stats_out != nullptr) p.stats_out[bl] = st16;   // every CTA of the image writes the same value
             }
           }
           __syncwarp();
@@ -479,15 +591,19 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       }
       const int kst = i % C::NK, slot = i % C::NS;
       const int qst = resident ? ul : up % C::NQ;
-      // resident stages complete exactly one phase; ring stages one phase per unit pass
-      ptx::mbar_wait(BAR(B_QFULL + qst), resident ? 0u : (uint32_t)((up / C::NQ) & 1));
-      ptx::mbar_wait(BAR(B_KFULL + kst), (uint32_t)((i / C::NK) & 1));
-      if (lane == 0) FX_TL(1, i);
-      if (i >= C::NS) {                              // the previous job on this slot is done with it
+      // the unit's Q tile (resident stages complete exactly one phase; ring stages one phase per unit pass): first job only
+      if (r.y & JF_FIRST) ptx::mbar_wait(BAR(B_QFULL + qst), resident ? 0u : (uint32_t)((up / C::NQ) & 1));
+      // this job's K tile, and the score slot: the previous job on it (i - NS) must be done with it
+      if (i >= C::NS) {
         const int prev = i - C::NS;
-        if (!is_main || prev < ns) ptx::mbar_wait(BAR(B_SFREE + slot), (uint32_t)((prev / C::NS) & 1));
-        else ptx::mbar_wait(BAR(B_PVDONE + slot), (uint32_t)(((prev - ns) / C::NS) & 1));
+        const bool by_sfree = !is_main || prev < ns;
+        ptx::mbar_wait2(BAR(B_KFULL + kst), (uint32_t)((i / C::NK) & 1),
+                        BAR((by_sfree ? B_SFREE : B_PVDONE) + slot),
+                        by_sfree ? (uint32_t)((prev / C::NS) & 1) : (uint32_t)(((prev - ns) / C::NS) & 1));
+      } else {
+        ptx::mbar_wait(BAR(B_KFULL + kst), (uint32_t)((i / C::NK) & 1));
       }
+      ptx::fence_proxy_async_smem();                 // K tile: cp.async (generic proxy) writes -> the UMMA's async-proxy reads
       ptx::tc_fence_after();
       if (lane == 0) FX_TL(2, i);
       const uint32_t qb = smem0 + qst * C::QSTAGE, kb = smem0 + C::OFF_K + kst * C::KSTAGE;
@@ -516,26 +632,19 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     }
   } else if (warp == 3) {
     // ============================== UMMA issuer: O = P V of every main job ==============================
-    // The whole warp waits for the V tile (every VFULL phase observed by the same threads, in order) and sets the spare
-    // column of the V atom to 1.0 for every real token: accumulator column D is the row sum.
     constexpr uint32_t idesc_pv = ptx::make_idesc_f16(128, C::DPV, false, true);
     for (int i = ns; i < njobs; ++i) {
       const int m = i - ns;
       const int st = m % C::NV, slot = i % C::NS, os = i % C::NO;
-      ptx::mbar_wait(BAR(B_VFULL + st), (uint32_t)((m / C::NV) & 1));
-      if (lane == 0) FX_TL(7, i);
-      {
-        unsigned char* vlast = smem_gen + C::OFF_V + st * C::VSTAGE;
-        constexpr int cc = D % 64;                 // spare column inside the atom
-        for (int rr = lane; rr < T; rr += 32)
-          *reinterpret_cast<__half*>(vlast + rr * 128 + ((((cc >> 3) ^ (rr & 7))) << 4) + (cc & 7) * 2) = __float2half(1.0f);
-        ptx::fence_proxy_async_smem();
-        __syncwarp();
-      }
-      ptx::mbar_wait(BAR(B_PREADY + slot), (uint32_t)((m / C::NS) & 1));
-      if (lane == 0) FX_TL(8, i);
-      if (m >= C::NO) ptx::mbar_wait(BAR(B_OFREE + os), (uint32_t)(((m / C::NO) - 1) & 1));
+      // the V tile, the group's P (written over S in tensor memory) and the output accumulator of 4 jobs ago
+      if (m >= C::NO)
+        ptx::mbar_wait3(BAR(B_VFULL + st), (uint32_t)((m / C::NV) & 1), BAR(B_PREADY + slot), (uint32_t)((m / C::NS) & 1),
+                        BAR(B_OFREE + os), (uint32_t)(((m / C::NO) - 1) & 1));
+      else
+        ptx::mbar_wait2(BAR(B_VFULL + st), (uint32_t)((m / C::NV) & 1), BAR(B_PREADY + slot), (uint32_t)((m / C::NS) & 1));
+      ptx::fence_proxy_async_smem();                 // V tile: cp.async (generic proxy) writes -> the UMMA's async-proxy reads
       ptx::tc_fence_after();
+      if (lane == 0) FX_TL(8, i);
       const uint32_t vb = smem0 + C::OFF_V + st * C::VSTAGE;
       if (elect_one()) {
 #pragma unroll
@@ -575,18 +684,20 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     int cur_li = -1;
     auto flush = [&]() {
       if (cur_li < 0) return;
-      double m = vmax, a = dsum, q = dsq;
+      StatPartial sp;
+      sp.vmax = 0.0; sp.sum = 0.0; sp.sumsq = 0.0; sp.pad = 1.0;
+      if (p.stat == PWW_STAT_MAX) {
+        sp.vmax = (double)key_f32(__reduce_max_sync(0xffffffffu, f32_key(vmax)));
+      } else {
+        double a = dsum, q = dsq;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-        a += __shfl_xor_sync(0xffffffffu, a, o);
-        q += __shfl_xor_sync(0xffffffffu, q, o);
+        for (int o = 16; o > 0; o >>= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o);
+          q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        sp.sum = a; sp.sumsq = q;
       }
-      if (lane == 0 && cur_li < kMaxLocal) {
-        StatPartial sp;
-        sp.vmax = m; sp.sum = a; sp.sumsq = q; sp.pad = 1.0;
-        s_part[sw][cur_li] = sp;
-      }
+      if (lane == 0 && cur_li < kMaxLocal) s_part[sw][cur_li] = sp;
       vmax = -INFINITY; dsum = 0.0; dsq = 0.0;
     };
 
@@ -642,9 +753,14 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
             sp.sum += s_part[w2][lane].sum;
             sp.sumsq += s_part[w2][lane].sumsq;
           }
-          p.partials[(int64_t)lbv * gridDim.x + blockIdx.x] = sp;
-          __threadfence();
-          atomicAdd(p.counters + lbv, 1u);
+          unsigned* word = p.counters + 64 + 2 * lbv;             // {max key, count}, see ld_acquire_gpu_u64
+          if (p.stat == PWW_STAT_MAX) {
+            asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(word), "r"(f32_key((float)sp.vmax)) : "memory");
+          } else {
+            p.partials[(int64_t)lbv * gridDim.x + blockIdx.x] = sp;
+          }
+          // release: the maximum / partial above is visible to whoever acquires the new count; nothing is waited for here
+          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(word + 1) : "memory");
         }
         if (lane == 0) FX_TL(12, 0);
         __syncwarp();
@@ -790,6 +906,7 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     const unsigned prev = atomicAdd(p.counters + kMaxBatch, 1u);
     if (prev == gridDim.x - 1u) {
       for (int b = 0; b < kMaxBatch + 1; ++b) p.counters[b] = 0u;
+      for (int b = 0; b < 2 * kMaxBatch; ++b) p.counters[64 + b] = 0u;      // sync words: maximum back to "-infinity", count 0
       __threadfence();
     }
   }
@@ -827,12 +944,8 @@ template <int D>
 cudaError_t launch_fused2(const XattnParams& x, const void* mpack, int64_t mpack_bs, int Bw, const int8_t* cidx,
                           cudaStream_t s) {
   using C = Cfg2<D>;
-  CUtensorMap tq, tk, tv, tm, to0, to1;
-  const int kB = x.k_bs > 0 ? x.B : 1;
-  if (!make_tmap_qfull(&tq, x.q, x.H * D, x.N, x.B, x.q_rs, x.q_bs) ||
-      !tc::make_tmap(&tk, x.k, D, x.H, x.T, kB, x.k_rs, x.k_bs, kTP) ||
-      !tc::make_tmap(&tv, x.v, D, x.H, x.T, kB, x.k_rs, x.k_bs, kTP))
-    return cudaErrorInvalidValue;
+  CUtensorMap tq, tm, to0, to1;
+  if (!make_tmap_qfull(&tq, x.q, x.H * D, x.N, x.B, x.q_rs, x.q_bs)) return cudaErrorInvalidValue;
   if (mpack != nullptr) {
     if (!make_tmap_mpack(&tm, mpack, x.N, Bw, mpack_bs)) return cudaErrorInvalidValue;
   } else {
@@ -872,8 +985,8 @@ cudaError_t launch_fused2(const XattnParams& x, const void* mpack, int64_t mpack
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (x.T == 77) return cudaLaunchKernelEx(&cfg, xattn_fused2_kernel<D, 77>, tq, tk, tv, tm, to0, to1, fp);
-  return cudaLaunchKernelEx(&cfg, xattn_fused2_kernel<D, 0>, tq, tk, tv, tm, to0, to1, fp);
+  if (x.T == 77) return cudaLaunchKernelEx(&cfg, xattn_fused2_kernel<D, 77>, tq, tm, to0, to1, fp);
+  return cudaLaunchKernelEx(&cfg, xattn_fused2_kernel<D, 0>, tq, tm, to0, to1, fp);
 }
 
 // Host replay of the job lists (test infrastructure): out[job] = {cta, i, kind, m, b, h, tile, biased, li, gi, up, ul,

@@ -37,7 +37,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for _ in range(20):          # warm clocks
     A.cross_attention(q, k, v, H, D ** -0.5, None, idx, _native.PWW_STAT_MAX, gs, packed=pk if biased else None)
 torch.cuda.synchronize()
-TAGS, ITS = 16, 64
+TAGS, ITS = 24, 64
 buf = torch.zeros(TAGS * ITS, dtype=torch.int64, device=dev)
 flush.fill_(1)
 torch.cuda.synchronize()
@@ -47,11 +47,13 @@ torch.cuda.synchronize()
 L.pww_debug_set_fused_timeline(None, 0)
 tab = buf.cpu().view(TAGS, ITS)
 t0 = int(tab[13, 0])
-f = lambda tag, it: (int(tab[tag, it]) - t0) if tab[tag, it] > 0 else -1   # noqa: E731
+f = lambda tag, it: (int(tab[tag, it]) - t0) if tab[tag, it] > 0 else -99999999   # noqa: E731
 print(f"B={B} biased={biased} cta={cta} N={N} H={H} D={D}; cycles since the post-prologue __syncthreads")
+print(f"kernel entry {f(21, 0)}; job table built {f(22, 0)}; TMEM allocated {f(23, 0)} (cycles relative to the post-prologue sync)")
+print(f"first Q load about to issue {f(15, 1)} {f(15, 2)}")
 print(f"grid barrier: start {f(10, 0)} end {f(11, 0)}; publish {f(12, 0)}; softmax groups done {f(14, 0)} {f(14, 1)}; kernel end {f(15, 0)}")
 print(" i | tma_issued  qfull  slot_free  s_issued | sready  math_done(pready/sfree)  epi_done | vfull  pready_seen  pv_issued")
 for it in range(ITS):
-    if tab[0, it] > 0 or tab[3, it] > 0:
+    if tab[0, it] > 0 or tab[3, it] > 0 or tab[16, it] > 0:
         print(f"{it:2d} | {f(0, it):7d} {f(1, it):7d} {f(2, it):7d} {f(3, it):7d} | {f(4, it):7d} {f(5, it):7d} {f(6, it):7d} | "
               f"{f(7, it):7d} {f(8, it):7d} {f(9, it):7d}")
