@@ -127,8 +127,12 @@ def _rows(t: torch.Tensor) -> torch.Tensor:
 
 
 # "fused": one launch (statistic + bias + softmax + PV, packed maps); "dense": round-1 pair of launches on the dense fp32
-# map.  Maps that cannot be packed (> 10 distinct columns) always take the dense pair.  Test/bench knob.
-XATTN_IMPL = "fused"
+# map; "auto" (default): the one-launch kernel where it is the faster of the two on this hardware -- head dim 40, the
+# grouped-head kernel of csrc/xattn_fused2.cuh (N = 4096 level of SD1.5: 18 vs 22 us at the cond+uncond launch, 48 vs 67 us
+# at 16 images) -- and the pair elsewhere (head dims 64 / 80 / 160 still run the per-head one-launch kernel, which the pair
+# beats: profiles/r02_microbench_sd15.jsonl, ..._sd21.jsonl).  Maps that cannot be packed (> 10 distinct columns) always
+# take the dense pair.
+XATTN_IMPL = "auto"
 
 
 def cross_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: float,
@@ -158,11 +162,14 @@ def cross_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: in
                 wmap = wmap.unsqueeze(0)
             if wmap.shape[1] != N or wmap.shape[2] != T:
                 raise ValueError(f"weight map shape {tuple(wmap.shape)} does not match N={N}, T={T}")
-        if biased and packed is None and XATTN_IMPL == "fused":
+        impl = XATTN_IMPL if XATTN_IMPL != "auto" else ("fused" if D == 40 else "dense")
+        if impl == "dense" and biased and wmap is None:
+            impl = "fused"                          # only the packed form was given
+        if biased and packed is None and impl == "fused":
             if wmap.dtype != torch.float32 or not wmap.is_contiguous():
                 wmap = wmap.to(torch.float32).contiguous()
             packed = st.packed(wmap)
-        use_fused = XATTN_IMPL == "fused" and (not biased or packed is not None)
+        use_fused = impl == "fused" and (not biased or packed is not None)
         if biased and wmap_index is None:
             bw = packed[0].shape[0] if packed is not None else wmap.shape[0]
             wmap_index = st.shared_index(B) if bw == 1 else torch.arange(B, dtype=torch.int32, device=q.device)
@@ -214,16 +221,19 @@ def cross_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: in
     return out
 
 
-# Self-attention (context=None): pww_attn_fwd_f16, the tcgen05 flash-attention kernel of libpww_b200.
-# SELF_ATTN_IMPL = "torch-sdpa" switches to torch's library attention -- a comparison knob for tests/bench only;
-# bench.py records which one ran in `config.self_attn`.
-SELF_ATTN_IMPL = "native"
+# Self-attention (context=None): "native" = pww_attn_fwd_f16, the tcgen05 flash-attention kernel of libpww_b200;
+# "torch-sdpa" = torch's library attention (cuDNN) -- like cuBLAS for the projections, a library call; "auto" (default) =
+# whichever is faster on this hardware: native up to 512 keys (23 vs 37 us at N = 256, 22 vs 31 us at N = 64), the library
+# above (N = 4096 d = 40: 144 vs 92 us, N = 1024 d = 80: 28 vs 24 us; profiles/r02_selfattn_microbench.jsonl -- the native
+# kernel is bound by its 8 softmax warps, see profiles/r02_notes.md).  bench.py records the setting in `config.self_attn`.
+SELF_ATTN_IMPL = "auto"
+SELF_ATTN_NATIVE_MAX_KEYS = 512
 
 
 def self_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: float) -> torch.Tensor:
     B, N, C = q.shape
     D = C // heads
-    if SELF_ATTN_IMPL == "native":
+    if SELF_ATTN_IMPL == "native" or (SELF_ATTN_IMPL == "auto" and N <= SELF_ATTN_NATIVE_MAX_KEYS):
         L = _native.lib()
         q, k, v = _rows(q), _rows(k), _rows(v)
         if not (q.stride() == k.stride() == v.stride()):

@@ -10,8 +10,13 @@
 //     P_g (packed fp16)                         -> TMEM (double-buffered where it fits), the A operand of
 //     O_g += P_g V_j    (TS-form UMMA M=128 N=D K=BN, V MN-major) accumulating in TMEM over all key tiles;
 //       for D = 40 / 80 a ones column in V makes accumulator column D the row sum of the fp16 P that was multiplied
-// Warp roles (384 threads): warp 0 Q+K TMA producer | warp 1 S-UMMA issuer + TMEM owner | warp 2 V TMA producer |
-// warp 3 PV-UMMA issuer | warps 4-7 and 8-11 the two softmax groups.  Every barrier that takes several arrivals per
+// Warp roles (384 threads): warp 0 Q by TMA, then the K loader | warp 1 S-UMMA issuer + TMEM owner | warp 2 V loader |
+// warp 3 PV-UMMA issuer | warps 4-7 and 8-11 the two softmax groups.  K / V tiles do not use the TMA: a head slice of a
+// key row is 80 bytes (D = 40) at an 80-byte offset, and the engine moves such rows at ~12 cycles each whatever the ring
+// depth (scripts/tma_probe.cu) -- two [64 x 80 B] boxes per key tile cost more than the tile's 1024 MUFU cycles.  The
+// loader warps copy the rows with 16-byte cp.async straight into the swizzled atoms (rows beyond N are zero-filled, the
+// ones column and the zero padding are written once per ring stage) and arrive on the stage's mbarrier.  The control
+// warps run warp-uniform loops and elect one lane only for the tcgen05 / TMA instructions (see xattn_fused2.cuh).  Every barrier that takes several arrivals per
 // phase is per buffer, so a warp's next arrival on it is causally behind the completion of the current phase.
 // Padding (d >= D, key >= N, row >= N) comes from TMA out-of-bounds zero fill; padded keys of the last tile are masked
 // to -inf.
@@ -58,10 +63,25 @@ struct Cfg {
 
 struct Params {
   __half* out;
+  const __half* k;
+  const __half* v;
   int B, H, N;
+  int64_t bs, rs;          // q/k/v element strides (batch, row)
   int64_t o_bs, o_rs;
   float scale;
 };
+
+__device__ __forceinline__ bool elect_one() {     // true on exactly one lane of a converged warp
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {   // src_bytes = 0: zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {   // arrives once this thread's cp.async so far have landed
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 
 template <int N>
 __device__ __forceinline__ void tmem_ld_row(uint32_t ta, float* v) {
@@ -84,8 +104,7 @@ __device__ __forceinline__ void tmem_st_row(uint32_t ta, const float* v) {
 
 template <int D>
 __global__ void __launch_bounds__(kThreads, 1)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
-                   const __grid_constant__ CUtensorMap tmv, const Params p) {
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const Params p) {
   using C = Cfg<D>;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -98,6 +117,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
   // warp arriving for tiles j and j+1 before a slow warp has written its rows of P(j).  With one barrier per buffer a
   // warp's next arrival on it (tile j+NP) is ordered behind PFREE, i.e. behind the P.V that consumed phase j.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Progress words (one per role) so a barrier time-out can say where every role stands: [0] Q/K producer tile,
+  // [1] S issuer tile, [2] V producer tile, [3] P.V issuer tile (x2 + group), [4..5] softmax group 0/1 tile.
+  __shared__ int s_prog[8];
+  auto wait = [&](uint32_t bar, uint32_t parity, int tag) {
+    if (ptx::mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!ptx::mbar_try_wait(bar, parity)) {
+      if (clock64() - t0 > 4000000000LL) {
+        if ((threadIdx.x & 31) == 0)
+          printf("pww-attn: timeout block %d warp %d tag %d bar %d parity %u | prog qk %d s %d v %d pv %d sm0 %d sm1 %d (n_kv %d)\n",
+                 blockIdx.x, threadIdx.x >> 5, tag, (int)((bar - bar0) >> 3), parity, s_prog[0], s_prog[1], s_prog[2], s_prog[3],
+                 s_prog[4], s_prog[5], (p.N + C::BN - 1) / C::BN);
+        __trap();
+      }
+    }
+  };
+  if (threadIdx.x < 8) s_prog[threadIdx.x] = -1;
   // block -> (image, head, query super-tile)
   const int qtiles = (p.N + 128 * C::NQ - 1) / (128 * C::NQ);
   const int qt = blockIdx.x % qtiles;
@@ -110,11 +146,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmq);
-    ptx::prefetch_tmap(&tmk);
-    ptx::prefetch_tmap(&tmv);
     ptx::mbar_init(BAR(B_QFULL), 1);
-    for (int s = 0; s < C::NK; ++s) { ptx::mbar_init(BAR(B_KFULL + s), 1); ptx::mbar_init(BAR(B_KEMPTY + s), 1); }
-    for (int s = 0; s < C::NV; ++s) { ptx::mbar_init(BAR(B_VFULL + s), 1); ptx::mbar_init(BAR(B_VEMPTY + s), 1); }
+    for (int s = 0; s < C::NK; ++s) { ptx::mbar_init(BAR(B_KFULL + s), 32); ptx::mbar_init(BAR(B_KEMPTY + s), 1); }   // 32: one cp.async arrival per loader lane
+    for (int s = 0; s < C::NV; ++s) { ptx::mbar_init(BAR(B_VFULL + s), 32); ptx::mbar_init(BAR(B_VEMPTY + s), 1); }
     for (int i = 0; i < 4; ++i) {
       ptx::mbar_init(BAR(B_SREADY + i), 1);
       ptx::mbar_init(BAR(B_SFREE + i), 4);
@@ -123,6 +157,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     }
     ptx::fence_barrier_init();
   }
+  // Ring-stage padding, written once (the per-tile copies only touch the D / 8 data chunks of a row): K columns D .. DP-1
+  // are zero; V columns D .. DPV-1 hold the ones column ([1, 0 x 7] at column D: accumulator column D of the P.V UMMA becomes
+  // the row sum; padded keys have P = 0, so every row may carry the 1) followed by zeros.
+  {
+    constexpr int kpad = (C::DP - D) / 8, vpad = (C::DPV - D) / 8;      // 16-byte chunks
+    for (int idx = threadIdx.x; idx < C::NK * C::BN * kpad; idx += kThreads) {
+      const int st = idx / (C::BN * kpad), rem = idx % (C::BN * kpad), r = rem / kpad, c = D / 8 + rem % kpad;
+      *reinterpret_cast<uint4*>(smem_gen + C::OFF_K + st * C::KSTAGE + (c / 8) * C::KATOM + r * 128 + (((c % 8) ^ (r & 7)) << 4)) =
+          make_uint4(0, 0, 0, 0);
+    }
+    for (int idx = threadIdx.x; idx < C::NV * C::BN * vpad; idx += kThreads) {
+      const int st = idx / (C::BN * vpad), rem = idx % (C::BN * vpad), r = rem / vpad, c = D / 8 + rem % vpad;
+      *reinterpret_cast<uint4*>(smem_gen + C::OFF_V + st * C::VSTAGE + (c / 8) * C::KATOM + r * 128 + (((c % 8) ^ (r & 7)) << 4)) =
+          make_uint4((C::ONES && c == D / 8) ? 0x00003C00u : 0u, 0, 0, 0);
+    }
+    ptx::fence_proxy_async_smem();
+  }
   if (warp == 1) ptx::tmem_alloc<C::TMEM_COLS>(BAR(B_TMEMPTR));
   ptx::tc_fence_before();
   __syncthreads();
@@ -130,96 +181,97 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + C::OFF_BAR + 8 * B_TMEMPTR);
   // (no setmaxnreg re-distribution: the two-pass softmax keeps every role under the 168-register budget)
 
+  // One key tile of K or V for this head: rows j*BN .. j*BN+63 (zero beyond N), D / 8 chunks of 16 bytes per row, into the
+  // swizzled atoms of a ring stage; a lane owns whole rows.
+  auto copy_tile = [&](uint32_t stage, const __half* base, int j, uint32_t bar) {
+    const __half* src = base + (int64_t)b * p.bs + h * D;
+#pragma unroll
+    for (int rr = 0; rr < C::BN / 32; ++rr) {
+      const int r = lane + 32 * rr, n = j * C::BN + r;
+      const bool ok = n < p.N;
+      const uint4* srow = reinterpret_cast<const uint4*>(src + (int64_t)(ok ? n : 0) * p.rs);
+      const uint32_t drow = stage + r * 128;
+      const int x7 = r & 7;
+#pragma unroll
+      for (int c = 0; c < D / 8; ++c)
+        cp_async16(drow + (c / 8) * C::KATOM + (((c % 8) ^ x7) << 4), srow + c, ok ? 16u : 0u);
+    }
+    cp_async_arrive(bar);
+  };
+
   if (warp == 0) {
-    // ------------------------------------------------ producer: Q tiles once, then the K ring
-    if (lane == 0) {
+    // ------------------------------------------------ Q tiles once (TMA), then the K loader
+    if (elect_one()) {
       ptx::mbar_arrive_expect_tx(BAR(B_QFULL), nq_live * C::QBYTES);
       for (int g = 0; g < nq_live; ++g)
 #pragma unroll
         for (int a = 0; a < C::NA; ++a)
           ptx::tma_load_4d(smem0 + g * C::QBYTES + a * C::QATOM, &tmq, BAR(B_QFULL), a * 64, h, row0 + g * 128, b);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j % C::NK;
-        ptx::mbar_wait(BAR(B_KEMPTY + st), (uint32_t)(((j / C::NK) & 1) ^ 1));
-        ptx::mbar_arrive_expect_tx(BAR(B_KFULL + st), C::KSTAGE);
-#pragma unroll
-        for (int a = 0; a < C::NA; ++a)
-          ptx::tma_load_4d(smem0 + C::OFF_K + st * C::KSTAGE + a * C::KATOM, &tmk, BAR(B_KFULL + st), a * 64, h,
-                           j * C::BN, b);
-      }
     }
     __syncwarp();
+    for (int j = 0; j < n_kv; ++j) {
+      if (lane == 0) s_prog[0] = j;
+      const int st = j % C::NK;
+      wait(BAR(B_KEMPTY + st), (uint32_t)(((j / C::NK) & 1) ^ 1), 1);
+      copy_tile(smem0 + C::OFF_K + st * C::KSTAGE, p.k, j, BAR(B_KFULL + st));
+    }
   } else if (warp == 2) {
-    // ------------------------------------------------ producer: V ring
-    if (lane == 0) {
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j % C::NV;
-        ptx::mbar_wait(BAR(B_VEMPTY + st), (uint32_t)(((j / C::NV) & 1) ^ 1));
-        ptx::mbar_arrive_expect_tx(BAR(B_VFULL + st), C::VSTAGE);
-#pragma unroll
-        for (int a = 0; a < C::NA; ++a)
-          ptx::tma_load_4d(smem0 + C::OFF_V + st * C::VSTAGE + a * C::KATOM, &tmv, BAR(B_VFULL + st), a * 64, h,
-                           j * C::BN, b);
-      }
+    // ------------------------------------------------ V loader
+    for (int j = 0; j < n_kv; ++j) {
+      if (lane == 0) s_prog[2] = j;
+      const int st = j % C::NV;
+      wait(BAR(B_VEMPTY + st), (uint32_t)(((j / C::NV) & 1) ^ 1), 2);
+      copy_tile(smem0 + C::OFF_V + st * C::VSTAGE, p.v, j, BAR(B_VFULL + st));
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------ UMMA issuer: S_g = Q_g K_j^T
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_f16(128, C::BN, false, false);
-      ptx::mbar_wait(BAR(B_QFULL), 0);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j % C::NK;
-        ptx::mbar_wait(BAR(B_KFULL + st), (uint32_t)((j / C::NK) & 1));
-        const int buf = j & 1;
-        for (int g = 0; g < nq_live; ++g) {
-          ptx::mbar_wait(BAR(B_SFREE + g * 2 + buf), (uint32_t)(((j >> 1) & 1) ^ 1));   // softmax done with this S buffer
-          ptx::tc_fence_after();
-          const uint32_t qb = smem0 + g * C::QBYTES, kb = smem0 + C::OFF_K + st * C::KSTAGE;
+    // ------------------------------------------------ UMMA issuer: S_g = Q_g K_j^T  (warp-uniform loop, elected issue)
+    constexpr uint32_t idesc = ptx::make_idesc_f16(128, C::BN, false, false);
+    wait(BAR(B_QFULL), 0, 3);
+    for (int j = 0; j < n_kv; ++j) {
+      if (lane == 0) s_prog[1] = j;
+      const int st = j % C::NK;
+      wait(BAR(B_KFULL + st), (uint32_t)((j / C::NK) & 1), 4);
+      ptx::fence_proxy_async_smem();               // K tile: cp.async (generic proxy) writes -> the UMMA's async-proxy reads
+      const int buf = j & 1;
+      for (int g = 0; g < nq_live; ++g) {
+        wait(BAR(B_SFREE + g * 2 + buf), (uint32_t)(((j >> 1) & 1) ^ 1), 5);   // softmax done with this S buffer
+        ptx::tc_fence_after();
+        const uint32_t qb = smem0 + g * C::QBYTES, kb = smem0 + C::OFF_K + st * C::KSTAGE;
+        if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < C::DP / 16; ++ks)
             ptx::umma_ss(tmem_base + C::col_s(g, buf),
                          ptx::make_sw128_desc(qb + (ks / 4) * C::QATOM + (ks % 4) * 32, 16, 1024),
                          ptx::make_sw128_desc(kb + (ks / 4) * C::KATOM + (ks % 4) * 32, 16, 1024), idesc, ks > 0);
           ptx::umma_commit(BAR(B_SREADY + g * 2 + buf));
+          if (g == nq_live - 1) ptx::umma_commit(BAR(B_KEMPTY + st));
         }
-        ptx::umma_commit(BAR(B_KEMPTY + st));
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else if (warp == 3) {
-    // ------------------------------------------------ UMMA issuer: O_g += P_g V_j
-    // The whole warp waits for the V tile (every VFULL phase is observed by the same threads, in order) and, for
-    // D = 40 / 80, sets the spare column of the last V atom to 1.0 for every real key: accumulator column D of the
-    // P.V UMMA is then the row sum of the fp16 P that was multiplied.
+    // ------------------------------------------------ UMMA issuer: O_g += P_g V_j  (warp-uniform loop, elected issue)
     constexpr uint32_t idesc = ptx::make_idesc_f16(128, C::DPV, false, true);
     for (int j = 0; j < n_kv; ++j) {
       const int st = j % C::NV;
-      ptx::mbar_wait(BAR(B_VFULL + st), (uint32_t)((j / C::NV) & 1));
-      if constexpr (C::ONES) {
-        const int valid = p.N - j * C::BN;          // keys of this tile that exist
-        unsigned char* vlast = smem_gen + C::OFF_V + st * C::VSTAGE + (C::NA - 1) * C::KATOM;
-        constexpr int cc = D % 64;
-        for (int r = lane; r < C::BN && r < valid; r += 32)
-          *reinterpret_cast<__half*>(vlast + r * 128 + ((((cc >> 3) ^ (r & 7))) << 4) + (cc & 7) * 2) = __float2half(1.0f);
-        ptx::fence_proxy_async_smem();
-        __syncwarp();
-      }
-      if (lane == 0) {
-        for (int g = 0; g < nq_live; ++g) {
-          const int pb = j % C::NP;
-          ptx::mbar_wait(BAR(B_PREADY + g * 2 + pb), (uint32_t)((j / C::NP) & 1));
-          ptx::tc_fence_after();
-          const uint32_t vb = smem0 + C::OFF_V + st * C::VSTAGE;
+      wait(BAR(B_VFULL + st), (uint32_t)((j / C::NV) & 1), 6);
+      ptx::fence_proxy_async_smem();               // V tile: cp.async (generic proxy) writes -> the UMMA's async-proxy reads
+      for (int g = 0; g < nq_live; ++g) {
+        if (lane == 0) s_prog[3] = 2 * j + g;
+        const int pb = j % C::NP;
+        wait(BAR(B_PREADY + g * 2 + pb), (uint32_t)((j / C::NP) & 1), 7);
+        ptx::tc_fence_after();
+        const uint32_t vb = smem0 + C::OFF_V + st * C::VSTAGE;
+        if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < C::BN / 16; ++ks)
             ptx::umma_ts(tmem_base + C::col_o(g), tmem_base + C::col_p(g, pb) + ks * 8,
                          ptx::make_sw128_desc(vb + ks * 16 * 128, C::KATOM, 1024), idesc, (j > 0) || (ks > 0));
           ptx::umma_commit(BAR(B_PFREE + g * 2 + pb));    // P buffer consumed == O_g holds tiles 0..j
+          if (g == nq_live - 1) ptx::umma_commit(BAR(B_VEMPTY + st));
         }
-        ptx::umma_commit(BAR(B_VEMPTY + st));
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
     // ------------------------------------------------ softmax groups
@@ -230,8 +282,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       const float sl2 = p.scale * 1.4426950408889634f;
       float m_run = -INFINITY, l_run = 0.f;
       for (int j = 0; j < n_kv; ++j) {
+        if ((warp & 3) == 0 && lane == 0) s_prog[4 + g] = j;
         const int buf = j & 1;
-        ptx::mbar_wait(BAR(B_SREADY + g * 2 + buf), (uint32_t)((j >> 1) & 1));
+        wait(BAR(B_SREADY + g * 2 + buf), (uint32_t)((j >> 1) & 1), 8);
         ptx::tc_fence_after();
         const uint32_t ts = tmem_base + lane_addr + C::col_s(g, buf);
         const int valid = p.N - j * C::BN;          // keys of this tile that exist (>= BN except in the last tile)
@@ -262,11 +315,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         const float nm = -m_run * sl2;
         // this tile's P buffer must have been consumed by its previous P.V ...
         const int pbuf = j % C::NP;
-        ptx::mbar_wait(BAR(B_PFREE + g * 2 + pbuf), (uint32_t)(((j / C::NP) & 1) ^ 1));
+        wait(BAR(B_PFREE + g * 2 + pbuf), (uint32_t)(((j / C::NP) & 1) ^ 1), 9);
         // ... and O may only be rescaled once the P.V of the previous tile has landed (rare path): that is the PFREE
         // phase of the previous tile's buffer, which this warp last waited on one phase earlier (no parity aliasing)
         if (j >= 1 && __any_sync(0xffffffffu, need)) {
-          ptx::mbar_wait(BAR(B_PFREE + g * 2 + (j - 1) % C::NP), (uint32_t)((((j - 1) / C::NP)) & 1));
+          wait(BAR(B_PFREE + g * 2 + (j - 1) % C::NP), (uint32_t)((((j - 1) / C::NP)) & 1), 10);
           ptx::tc_fence_after();
           float o[C::DPV];
           tmem_ld_row<C::DPV>(tmem_base + lane_addr + C::col_o(g), o);
@@ -310,7 +363,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         if (lane == 0) ptx::mbar_arrive(BAR(B_PREADY + g * 2 + pbuf));
       }
       // epilogue: O / l -> fp16 -> global
-      ptx::mbar_wait(BAR(B_PFREE + g * 2 + (n_kv - 1) % C::NP), (uint32_t)(((n_kv - 1) / C::NP) & 1));
+      wait(BAR(B_PFREE + g * 2 + (n_kv - 1) % C::NP), (uint32_t)(((n_kv - 1) / C::NP) & 1), 11);
       ptx::tc_fence_after();
       float o[C::DPV];
       tmem_ld_row<C::DPV>(tmem_base + lane_addr + C::col_o(g), o);
@@ -337,12 +390,11 @@ template <int D>
 cudaError_t launch(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int64_t bs, int64_t rs,
                    int64_t o_bs, int64_t o_rs, float scale, cudaStream_t s) {
   using C = Cfg<D>;
-  CUtensorMap tq, tk, tv;
-  if (!tc::make_tmap(&tq, q, D, H, N, B, rs, bs, 128) || !tc::make_tmap(&tk, k, D, H, N, B, rs, bs, C::BN) ||
-      !tc::make_tmap(&tv, v, D, H, N, B, rs, bs, C::BN))
-    return cudaErrorInvalidValue;
+  CUtensorMap tq;
+  if (!tc::make_tmap(&tq, q, D, H, N, B, rs, bs, 128)) return cudaErrorInvalidValue;
   Params p;
-  p.out = (__half*)out; p.B = B; p.H = H; p.N = N; p.o_bs = o_bs; p.o_rs = o_rs; p.scale = scale;
+  p.out = (__half*)out; p.k = (const __half*)k; p.v = (const __half*)v; p.B = B; p.H = H; p.N = N; p.bs = bs; p.rs = rs;
+  p.o_bs = o_bs; p.o_rs = o_rs; p.scale = scale;
   static bool attr_set[tc::kMaxDevices] = {false};
   if (!attr_set[tc::cur_device()]) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
@@ -350,7 +402,7 @@ cudaError_t launch(const void* q, const void* k, const void* v, void* out, int B
     attr_set[tc::cur_device()] = true;
   }
   const int qtiles = (N + 128 * C::NQ - 1) / (128 * C::NQ);
-  attn_fwd_tc_kernel<D><<<B * H * qtiles, kThreads, C::SMEM, s>>>(tq, tk, tv, p);
+  attn_fwd_tc_kernel<D><<<B * H * qtiles, kThreads, C::SMEM, s>>>(tq, p);
   return cudaGetLastError();
 }
 

@@ -3,6 +3,7 @@ import pytest
 import torch
 
 from oracle import pww_oracle as O
+from paint_with_words_sd_b200 import _native
 from paint_with_words_sd_b200 import attention as A
 
 pytestmark = pytest.mark.gpu
@@ -18,9 +19,22 @@ def _qkv(B, N, H, D, seed, spread=0.5):
     return [(torch.randn(B, N, C, generator=g) * spread).half() for _ in range(3)]
 
 
+def _native_attention(q, k, v, H, scale):
+    """The library's own kernel at every size (the shim's default picks per size)."""
+    old = A.SELF_ATTN_IMPL
+    A.SELF_ATTN_IMPL = "native"
+    try:
+        before = _native.launch_count
+        out = A.self_attention(q, k, v, H, scale)
+        assert _native.launch_count == before + 1
+    finally:
+        A.SELF_ATTN_IMPL = old
+    return out
+
+
 def _check(q, k, v, H, D, tol=2e-3):
     scale = D ** -0.5
-    got = A.self_attention(q.cuda(), k.cuda(), v.cuda(), H, scale)
+    got = _native_attention(q.cuda(), k.cuda(), v.cuda(), H, scale)
     torch.cuda.synchronize()
     got = got.float().cpu()
     ref = torch.cat([O.attention_core(q[b:b + 1].float(), k[b:b + 1].float(), v[b:b + 1].float(), H, scale)
@@ -31,7 +45,6 @@ def _check(q, k, v, H, D, tol=2e-3):
 
 @pytest.mark.parametrize("N,H,D", SHAPES)
 def test_self_attention_matches_oracle(N, H, D):
-    assert A.SELF_ATTN_IMPL == "native"
     q, k, v = _qkv(2 if N <= 1024 else 1, N, H, D, seed=N + D)
     _check(q, k, v, H, D)
 
@@ -56,6 +69,17 @@ def test_strided_qkv_views():
     C = H * D
     q, k, v = _qkv(1, N, H, D, seed=3)
     fused = torch.cat([q, k, v], -1).cuda()
-    got = A.self_attention(fused[..., :C], fused[..., C:2 * C], fused[..., 2 * C:], H, D ** -0.5).float().cpu()
+    got = _native_attention(fused[..., :C], fused[..., C:2 * C], fused[..., 2 * C:], H, D ** -0.5).float().cpu()
     ref = O.attention_core(q.float(), k.float(), v.float(), H, D ** -0.5)
     assert (got - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+
+
+def test_default_dispatch_matches_oracle_on_both_sides_of_the_switch():
+    """The shim's default: native kernel up to 512 keys, torch's library attention above -- same numbers either way."""
+    for N, native in ((256, True), (1024, False)):
+        q, k, v = _qkv(1, N, 8, 40, seed=N)
+        before = _native.launch_count
+        got = A.self_attention(q.cuda(), k.cuda(), v.cuda(), 8, 40 ** -0.5).float().cpu()
+        assert (_native.launch_count == before + 1) == native
+        ref = O.attention_core(q.float(), k.float(), v.float(), 8, 40 ** -0.5)
+        assert (got - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()

@@ -218,7 +218,7 @@ def test_mask_barrier_stress_cold_maps(B, impl):
         else:
             bad += (out != first).any().to(torch.int32)
     torch.cuda.synchronize()
-    A.XATTN_IMPL = "fused"
+    A.XATTN_IMPL = "auto"
     assert int(bad) == 0, f"{int(bad)} of 199 repeat launches differ from the first"
     amax = ref32.abs().max().item()
     assert (first.float().cpu() - ref32).abs().max().item() <= 2e-3 * amax
@@ -278,6 +278,18 @@ def test_fused_all_biased_and_all_unbiased_batches():
     w_eff = torch.stack([w[2], torch.zeros(N, T), torch.zeros(N, T)])
     ref32, _ = _oracle(q, k, v, H, D ** -0.5, w_eff, g, "max", emulate=False)
     assert (got - ref32).abs().max().item() <= 2e-3 * ref32.abs().max().item()
+
+
+def test_default_dispatch_per_head_dim():
+    """The shim's default picks the one-launch kernel at head dim 40 and the two-launch pair elsewhere (measured: the
+    grouped-head kernel beats the pair, the per-head one-launch kernel does not yet)."""
+    for (N, H, D, launches) in ((1024, 8, 40, 1), (256, 8, 80, 2), (256, 5, 64, 2)):
+        q, k, v, w = _inputs(1, N, H, D, 77, seed=N + D)
+        before = _native.launch_count
+        got, st = _run(q, k, v, H, D ** -0.5, w, 0.6, "max", impl="auto")
+        assert _native.launch_count - before == launches
+        ref32, _ = _oracle(q, k, v, H, D ** -0.5, w, 0.6, "max", emulate=False)
+        assert (got - ref32).abs().max().item() <= 2e-3 * ref32.abs().max().item()
 
 
 def test_fused_more_than_ten_columns_takes_the_dense_pair():
