@@ -1,6 +1,6 @@
 """Summarise ncu --set full reports of the cross-attention kernels (read here, no GPU needed):
-python scripts/ncu_summary.py gpurun_out/r01b_xattn_B2.ncu-rep gpurun_out/r01b_xattn_B16.ncu-rep
-writes profiles/r01_xattn_ncu_full_summary.txt and profiles/r01_xattn_traffic.json."""
+python scripts/ncu_summary.py r02 gpurun_out/r02_xattn_B2.ncu-rep gpurun_out/r02_xattn_B16.ncu-rep
+writes profiles/<tag>_xattn_ncu_full_summary.txt and profiles/<tag>_xattn_traffic.json."""
 import csv
 import io
 import json
@@ -36,13 +36,14 @@ def rows_of(rep):
 
 lines = ["ncu --set full --clock-control none; scripts/profile_xattn.py B biased (N=4096,H=8,D=40,T=77), rotating buffers"]
 traffic = {}
-for rep in sys.argv[1:]:
+TAG = sys.argv[1]
+for rep in sys.argv[2:]:
     tag = re.search(r"_B(\d+)", rep).group(1)
     hdr, units, rows = rows_of(rep)
     ix = {h: i for i, h in enumerate(hdr)}
     for r in rows:
         name = r[ix["Kernel Name"]]
-        kind = "stats" if "stats" in name else "fwd"
+        kind = "stats" if "stats" in name else ("fused" if "fused" in name else "fwd")
         lines.append(f"--- B={tag} {kind}: {name[:110]}")
         vals = {}
         for m in METRICS:
@@ -56,6 +57,6 @@ for rep in sys.argv[1:]:
             dur /= 1e3
         traffic[f"B{tag}_{kind}"] = {"dram_read_bytes": rd, "dram_write_bytes": wr, "traffic_bytes": rd + wr,
                                      "duration_us_under_ncu": dur}
-open(os.path.join(ROOT, "profiles", "r01_xattn_ncu_full_summary.txt"), "w").write("\n".join(lines) + "\n")
-json.dump(traffic, open(os.path.join(ROOT, "profiles", "r01_xattn_traffic.json"), "w"), indent=1)
+open(os.path.join(ROOT, "profiles", f"{TAG}_xattn_ncu_full_summary.txt"), "w").write("\n".join(lines) + "\n")
+json.dump(traffic, open(os.path.join(ROOT, "profiles", f"{TAG}_xattn_traffic.json"), "w"), indent=1)
 print("\n".join(lines))
