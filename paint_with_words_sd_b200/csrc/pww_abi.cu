@@ -360,6 +360,8 @@ int pww_debug_fused2_schedule(int B, int H, int G, int tiles, int grid, const in
   return pww::fx2::fused2_schedule_host(B, H, G, tiles, grid, wmap_index, out, max_jobs);
 }
 // Test infrastructure: device buffer of grid * (2 + 1024) uint32 the grouped-head kernel copies every CTA's job table to.
+// Heads per unit of the grouped-head kernel (a build-time constant).
+int pww_debug_fused2_heads_per_unit(void) { return pww::fx2::Cfg2<40>::G; }
 int pww_debug_set_fused_jobs_dump(void* device_buffer) {
   pww::fx::debug_jobs_dump() = (unsigned*)device_buffer;
   return PWW_OK;

@@ -32,8 +32,12 @@ using namespace fx;   // unit walk, helpers and constants shared with the per-he
 template <int D>
 struct Cfg2 {
   static_assert(D == 40, "the grouped-head kernel is built for head dim 40");
-  static constexpr int G = 4;                       // heads per unit: G * D = 160 columns
-  static constexpr int NAQ = 3;                     // 64-column atoms of the unit's Q tile (192 columns cover the 160)
+#ifndef PWW_FX2_G
+#define PWW_FX2_G 2
+#endif
+  static constexpr int G = PWW_FX2_G;               // heads per unit (2: 80 columns inside 2 atoms; 4: 160 columns inside 3)
+  static_assert(G == 2 || G == 4, "heads per unit");
+  static constexpr int NAQ = (G == 4) ? 3 : 2;      // 64-column atoms that cover the unit's G * D columns wherever they start
   static constexpr int DP = (D + 15) / 16 * 16;
   static constexpr int KSTEPS = DP / 16;            // 16-column blocks per head: 3 (a head starts 0 or 8 columns into its first block)
   static constexpr bool ONES = true;                // row sums ride on the P.V UMMA (spare V column = 1.0)
@@ -193,7 +197,7 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   const uint32_t bar0 = smem0 + C::OFF_BAR;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   constexpr int B_QFULL = 0, B_QEMPTY = 2, B_KFULL = 4, B_KEMPTY = 7, B_VFULL = 10, B_VEMPTY = 13, B_SREADY = 16,
-                B_SFREE = 20, B_PREADY = 24, B_PVDONE = 28, B_OFREE = 32, B_COEF = 36, B_TMEMPTR = 38;
+                B_SFREE = 20, B_PREADY = 24, B_PVDONE = 28, B_OFREE = 32, B_COEF = 36, B_TMEMPTR = 38, B_STATS = 39;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = TT ? TT : p.T;
   int u0, u1;
@@ -211,6 +215,8 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   __shared__ float s_coef[kMaxLocal];             // g(sigma) * statistic of the CTA's local biased images
   __shared__ StatPartial s_part[16][kMaxLocal];   // [softmax warp][local biased image]
   __shared__ uint2 s_jobs[kMaxJobs];
+  __shared__ unsigned s_key[16][kMaxLocal];        // max statistic: order-preserving keys of the softmax warps' partial maxima
+  __shared__ signed char s_cidx[kMaxLocal][kTP];   // token -> dictionary column of the CTA's local biased images
   __shared__ int s_img0[kMaxBatch], s_widx0[kMaxBatch], s_pre;   // producer warp's own copy of the partition; early Q loads
 
   if (warp == 0) {
@@ -346,6 +352,7 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     StatPartial sp;
     sp.vmax = -INFINITY; sp.sum = 0.0; sp.sumsq = 0.0; sp.pad = 0.0;
     s_part[i / kMaxLocal][i % kMaxLocal] = sp;
+    s_key[i / kMaxLocal][i % kMaxLocal] = 0u;      // key 0 is below every real number
   }
   // K / V ring stages, once: zero rows T..79 (the per-job copies never touch them); V chunk column 5 = [1.0, 0 x 7] for real
   // tokens -- the spare column that makes accumulator column D of the P.V UMMA the row sum -- and zero for padded ones.
@@ -382,6 +389,7 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     }
     ptx::mbar_init(BAR(B_COEF + 0), 1);
     ptx::mbar_init(BAR(B_COEF + 1), 1);
+    ptx::mbar_init(BAR(B_STATS), 16);             // every softmax warp has written its statistic partials
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -464,11 +472,48 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       copy_kv(smem0 + C::OFF_K + st * C::KSTAGE, p.k, r.x, sh, sh ? 0 : 5, BAR(B_KFULL + st));
     }
   } else if (warp == 2) {
-    // ============================== loader: V tiles of the main jobs ==============================
+    // ============================== loader: V tiles of the main jobs (+ statistic publish) ==============================
+    auto publish = [&]() {
+      const int nl = s_nl;
+      if (p.stat == PWW_STAT_MAX) {
+        // the maximum is order independent: 16 keys -> one warp reduction -> one atomic max on the image's word
+        for (int l = 0; l < nl && l < kMaxLocal; ++l) {
+          const unsigned k = __reduce_max_sync(0xffffffffu, lane < 16 ? s_key[lane][l] : 0u);
+          if (lane == 0) {
+            unsigned* word = p.counters + 64 + 2 * s_lb[l];        // {max key, count}, see ld_acquire_gpu_u64
+            asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(word), "r"(k) : "memory");
+            // release: the maximum above is visible to whoever acquires the new count; nothing is waited for here
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(word + 1) : "memory");
+          }
+        }
+      } else if (lane < nl && lane < kMaxLocal) {
+        // std: fixed-order sums of the 16 warps' partials into this CTA's slot (the waiters add the slots in CTA order)
+        const int lbv = s_lb[lane];
+        StatPartial sp = s_part[0][lane];
+        for (int w2 = 1; w2 < 16; ++w2) {
+          sp.sum += s_part[w2][lane].sum;
+          sp.sumsq += s_part[w2][lane].sumsq;
+        }
+        p.partials[(int64_t)lbv * gridDim.x + blockIdx.x] = sp;
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.counters + 64 + 2 * lbv + 1) : "memory");
+      }
+      if (lane == 0) FX_TL(12, 0);
+      __syncwarp();
+    };
     for (int i = ns; i < njobs; ++i) {
       const int m = i - ns, st = m % C::NV;
+      if (m == C::NV && ns > 0) {
+        // ---- publish the CTA's statistic partials (the first NV tiles of V are already on their way): one lane per local
+        //      image reduces the 16 softmax warps' partials in a fixed order, folds them into the image's word, arrives ----
+        ptx::mbar_wait(BAR(B_STATS), 0);
+        publish();
+      }
       ptx::mbar_wait(BAR(B_VEMPTY + st), (uint32_t)(((m / C::NV) & 1) ^ 1));
       copy_kv(smem0 + C::OFF_V + st * C::VSTAGE, p.v, s_jobs[i].x, 0, -1, BAR(B_VFULL + st));
+    }
+    if (ns > 0 && njobs - ns <= C::NV) {           // fewer main jobs than ring stages: not published inside the loop
+      ptx::mbar_wait(BAR(B_STATS), 0);
+      publish();
     }
   } else if (warp == 1) {
     // ============================== UMMA issuer: S of every job (+ grid barrier and the bias operand) ==============================
@@ -492,12 +537,31 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       }
     }
     const unsigned long long* sync_words = reinterpret_cast<const unsigned long long*>(p.counters + 64);
-    for (int i = 0; i < njobs; ++i) {
+    // everything the bias operand needs besides the statistic is fetched now, not after the barrier
+    const float gsig = (nb > 0 && p.g_sigma != nullptr) ? __ldg(p.g_sigma) : 0.f;
+    {
+      const int nl = s_nl;
+      for (int idx = lane; idx < nl * kTP && idx < kMaxLocal * kTP; idx += 32) {
+        const int l = idx / kTP, t = idx - l * kTP;
+        s_cidx[l][t] = (t < T) ? fp.cidx[(int64_t)s_widx[s_lb[l]] * kTP + t] : (signed char)-1;
+      }
+      __syncwarp();
+    }
+    // Jobs are issued in PAIRS where two consecutive jobs are of the same kind (one per softmax group): the loop's fixed
+    // cost -- table read, barrier probes, fences, elect, warp sync, ~1000 cycles of a single warp's dependent chain -- is
+    // paid once per two heads, and both groups get their S at the same time.
+    for (int i = 0; i < njobs;) {
       const uint2 r = s_jobs[i];
-      const int b = r.x & 0xff, h = (r.x >> 8) & 0xff;
+      const int b = r.x & 0xff;
       const bool is_main = (r.y & JF_MAIN) != 0, biased = (r.y & JF_BIASED) != 0;
-      const int li = (r.y >> 4) & 3, ul = (r.y >> 8) & 0xff;
-      if (r.y & JF_FIRST) ++up;
+      const int li = (r.y >> 4) & 3;
+      int npair = 1;
+      if (i + 1 < njobs) {
+        const unsigned y1 = s_jobs[i + 1].y, km = JF_MAIN | JF_BIASED;
+        bool same = (r.y & km) == (y1 & km);
+        if (same && (r.y & km) == km) same = li == (int)((y1 >> 4) & 3);        // biased softmax jobs: same image's bias operand
+        if (same) npair = 2;
+      }
       if (is_main && biased) {
         if (!stats_ready) {
           // ---- grid barrier: every CTA owning units of my biased images has published its partial ----
@@ -549,7 +613,7 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
                 rr = sqrt(var > 0.0 ? var : 0.0);
               }
               const float st16 = round_to_f16((float)rr);         // qk.max() / qk.std() return fp16 in the reference
-              s_coef[l] = __ldg(p.g_sigma) * st16;
+              s_coef[l] = gsig * st16;
               if (p.stats_out != nullptr) p.stats_out[bl] = st16;   // every CTA of the image writes the same value
             }
           }
@@ -569,12 +633,12 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
           const __half xh = __float2half_rn(x);
           const __half xl = __float2half_rn(x - __half2float(xh));
           unsigned char* tile = smem_gen + C::OFF_COEF + buf * kCoefTile;
-          const int8_t* ci = fp.cidx + (int64_t)s_widx[b] * kTP;
+          const signed char* ci = s_cidx[li < kMaxLocal ? li : 0];
           for (int t = lane; t < kTP; t += 32) {
             uint4* rowp = reinterpret_cast<uint4*>(tile + t * 64);
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) rowp[ch] = make_uint4(0, 0, 0, 0);
-            const int rc = (t < T) ? (int)ci[t] : -1;
+            const int rc = (int)ci[t];
             if (rc >= 0 && rc < kRC) {
               auto put = [&](int k, __half v) {
                 *reinterpret_cast<__half*>(tile + t * 64 + ((((k >> 3) ^ ((t >> 1) & 3))) << 4) + (k & 7) * 2) = v;
@@ -589,46 +653,63 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
           cur_li = li;
         }
       }
-      const int kst = i % C::NK, slot = i % C::NS;
-      const int qst = resident ? ul : up % C::NQ;
-      // the unit's Q tile (resident stages complete exactly one phase; ring stages one phase per unit pass): first job only
-      if (r.y & JF_FIRST) ptx::mbar_wait(BAR(B_QFULL + qst), resident ? 0u : (uint32_t)((up / C::NQ) & 1));
-      // this job's K tile, and the score slot: the previous job on it (i - NS) must be done with it
-      if (i >= C::NS) {
-        const int prev = i - C::NS;
-        const bool by_sfree = !is_main || prev < ns;
-        ptx::mbar_wait2(BAR(B_KFULL + kst), (uint32_t)((i / C::NK) & 1),
-                        BAR((by_sfree ? B_SFREE : B_PVDONE) + slot),
-                        by_sfree ? (uint32_t)((prev / C::NS) & 1) : (uint32_t)(((prev - ns) / C::NS) & 1));
-      } else {
-        ptx::mbar_wait(BAR(B_KFULL + kst), (uint32_t)((i / C::NK) & 1));
+      int qst_t[2] = {0, 0};
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (t >= npair) break;
+        const int it = i + t;
+        const uint2 rt = s_jobs[it];
+        const int kst = it % C::NK, slot = it % C::NS;
+        if (rt.y & JF_FIRST) ++up;
+        const int qst = resident ? (int)((rt.y >> 8) & 0xff) : up % C::NQ;
+        qst_t[t] = qst;
+        // the unit's Q tile (resident stages complete exactly one phase; ring stages one phase per unit pass): first job only
+        if (rt.y & JF_FIRST) ptx::mbar_wait(BAR(B_QFULL + qst), resident ? 0u : (uint32_t)((up / C::NQ) & 1));
+        // this job's K tile, and the score slot: the previous job on it (it - NS) must be done with it
+        if (it >= C::NS) {
+          const int prev = it - C::NS;
+          const bool by_sfree = !is_main || prev < ns;
+          ptx::mbar_wait2(BAR(B_KFULL + kst), (uint32_t)((it / C::NK) & 1),
+                          BAR((by_sfree ? B_SFREE : B_PVDONE) + slot),
+                          by_sfree ? (uint32_t)((prev / C::NS) & 1) : (uint32_t)(((prev - ns) / C::NS) & 1));
+        } else {
+          ptx::mbar_wait(BAR(B_KFULL + kst), (uint32_t)((it / C::NK) & 1));
+        }
       }
-      ptx::fence_proxy_async_smem();                 // K tile: cp.async (generic proxy) writes -> the UMMA's async-proxy reads
+      ptx::fence_proxy_async_smem();                 // K tiles: cp.async (generic proxy) writes -> the UMMA's async-proxy reads
       ptx::tc_fence_after();
       if (lane == 0) FX_TL(2, i);
-      const uint32_t qb = smem0 + qst * C::QSTAGE, kb = smem0 + C::OFF_K + kst * C::KSTAGE;
-      const int atom0 = ((h / C::G) * C::G * D) / 64;
-      const int blk0 = (h * D) / 16;                 // first 16-column block of the head inside the query row
       if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < C::KSTEPS; ++ks) {
-          const int blk = blk0 + ks;
-          const uint32_t qa = qb + (uint32_t)(blk / 4 - atom0) * kQAtom + (uint32_t)(blk % 4) * 32u;
-          ptx::umma_ss(tmem_base + C::col_s(slot), ptx::make_sw128_desc(qa, 16, 1024),
-                       ptx::make_sw128_desc(kb + ks * 32, 16, 1024), idesc_qk, ks > 0);
-        }
-        if (is_main && biased) {
-          const uint32_t ma = qb + C::QBYTES, ca = smem0 + C::OFF_COEF + (li & 1) * kCoefTile;
+        for (int t = 0; t < 2; ++t) {
+          if (t >= npair) break;
+          const int it = i + t;
+          const uint2 rt = s_jobs[it];
+          const int h = (rt.x >> 8) & 0xff, kst = it % C::NK, slot = it % C::NS, qst = qst_t[t];
+          const uint32_t qb = smem0 + qst * C::QSTAGE, kb = smem0 + C::OFF_K + kst * C::KSTAGE;
+          const int atom0 = ((h / C::G) * C::G * D) / 64;
+          const int blk0 = (h * D) / 16;             // first 16-column block of the head inside the query row
 #pragma unroll
-          for (int ks = 0; ks < kMW / 16; ++ks)
-            ptx::umma_ss(tmem_base + C::col_s(slot), make_sw64_desc(ma + ks * 32), make_sw64_desc(ca + ks * 32), idesc_qk, true);
+          for (int ks = 0; ks < C::KSTEPS; ++ks) {
+            const int blk = blk0 + ks;
+            const uint32_t qa = qb + (uint32_t)(blk / 4 - atom0) * kQAtom + (uint32_t)(blk % 4) * 32u;
+            ptx::umma_ss(tmem_base + C::col_s(slot), ptx::make_sw128_desc(qa, 16, 1024),
+                         ptx::make_sw128_desc(kb + ks * 32, 16, 1024), idesc_qk, ks > 0);
+          }
+          if (is_main && biased) {
+            const uint32_t ma = qb + C::QBYTES, ca = smem0 + C::OFF_COEF + (li & 1) * kCoefTile;
+#pragma unroll
+            for (int ks = 0; ks < kMW / 16; ++ks)
+              ptx::umma_ss(tmem_base + C::col_s(slot), make_sw64_desc(ma + ks * 32), make_sw64_desc(ca + ks * 32), idesc_qk, true);
+          }
+          ptx::umma_commit(BAR(B_SREADY + slot));
+          ptx::umma_commit(BAR(B_KEMPTY + kst));     // the K tile is dead once S exists
+          if ((rt.y & JF_LAST) && !resident) ptx::umma_commit(BAR(B_QEMPTY + qst));   // ... and so is the unit's Q tile after its last head
+          FX_TL(3, it);
         }
-        ptx::umma_commit(BAR(B_SREADY + slot));
-        ptx::umma_commit(BAR(B_KEMPTY + kst));       // the K tile is dead once S exists
-        if ((r.y & JF_LAST) && !resident) ptx::umma_commit(BAR(B_QEMPTY + qst));   // ... and so is the unit's Q tile after its last head
-        FX_TL(3, i);
       }
       __syncwarp();
+      i += npair;
     }
   } else if (warp == 3) {
     // ============================== UMMA issuer: O = P V of every main job ==============================
@@ -684,10 +765,9 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     int cur_li = -1;
     auto flush = [&]() {
       if (cur_li < 0) return;
-      StatPartial sp;
-      sp.vmax = 0.0; sp.sum = 0.0; sp.sumsq = 0.0; sp.pad = 1.0;
       if (p.stat == PWW_STAT_MAX) {
-        sp.vmax = (double)key_f32(__reduce_max_sync(0xffffffffu, f32_key(vmax)));
+        const unsigned kmax = __reduce_max_sync(0xffffffffu, f32_key(vmax));
+        if (lane == 0 && cur_li < kMaxLocal) s_key[sw][cur_li] = kmax;
       } else {
         double a = dsum, q = dsq;
 #pragma unroll
@@ -695,9 +775,12 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
           a += __shfl_xor_sync(0xffffffffu, a, o);
           q += __shfl_xor_sync(0xffffffffu, q, o);
         }
-        sp.sum = a; sp.sumsq = q;
+        if (lane == 0 && cur_li < kMaxLocal) {
+          StatPartial sp;
+          sp.vmax = 0.0; sp.sum = a; sp.sumsq = q; sp.pad = 1.0;
+          s_part[sw][cur_li] = sp;
+        }
       }
-      if (lane == 0 && cur_li < kMaxLocal) s_part[sw][cur_li] = sp;
       vmax = -INFINITY; dsum = 0.0; dsq = 0.0;
     };
 
@@ -741,30 +824,7 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     }
     if (ns > 0) {
       flush();
-      ptx::named_bar_sync(9, 512);               // all 16 softmax warps have written their partials
-      if (sw == 0) {
-        // publish: one lane per local image reduces the 16 warps in a fixed order, writes the CTA's slot, arrives
-        const int nl = s_nl;
-        if (lane < nl && lane < kMaxLocal) {
-          const int lbv = s_lb[lane];
-          StatPartial sp = s_part[0][lane];
-          for (int w2 = 1; w2 < 16; ++w2) {
-            sp.vmax = fmax(sp.vmax, s_part[w2][lane].vmax);
-            sp.sum += s_part[w2][lane].sum;
-            sp.sumsq += s_part[w2][lane].sumsq;
-          }
-          unsigned* word = p.counters + 64 + 2 * lbv;             // {max key, count}, see ld_acquire_gpu_u64
-          if (p.stat == PWW_STAT_MAX) {
-            asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(word), "r"(f32_key((float)sp.vmax)) : "memory");
-          } else {
-            p.partials[(int64_t)lbv * gridDim.x + blockIdx.x] = sp;
-          }
-          // release: the maximum / partial above is visible to whoever acquires the new count; nothing is waited for here
-          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(word + 1) : "memory");
-        }
-        if (lane == 0) FX_TL(12, 0);
-        __syncwarp();
-      }
+      warp_arrive(BAR(B_STATS));                   // the V loader warp publishes the CTA's partials (off this warp's path)
     }
 
     // ---- main jobs ----

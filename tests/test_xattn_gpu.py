@@ -351,7 +351,7 @@ def test_grouped_head_job_table_built_on_the_device_equals_the_host_replay(B, N,
     Dump the device tables and compare them job by job."""
     import ctypes
     L = _native.lib()
-    D, T, G = 40, 77, 4
+    D, T, G = 40, 77, L.pww_debug_fused2_heads_per_unit()
     q, k, v, w = _inputs(B, N, H, D, T, seed=B + N + H)
     nbw = max(idx) + 1
     tiles = (N + 127) // 128
