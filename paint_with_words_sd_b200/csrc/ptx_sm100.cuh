@@ -52,9 +52,11 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Wait for the phase with the given parity to complete.  Bounded: traps after ~10 s (long enough for instrumented profiler replays).
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// Wait for the phase with the given parity to complete.  Bounded: traps after ~10 s (long enough for instrumented profiler
+// replays).  The spinning / time-out / printf path is OUT OF LINE: inlined at every wait it was a fifth of the one-launch
+// kernel's 200 KB of code, and at the denoising loop's launch sizes every role runs its code once or twice per launch --
+// instruction-cache misses were 20 % of that kernel's stall samples (profiles/r02_notes.md).
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 20000000000LL) {
@@ -62,6 +64,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
 }
 
 // Wait for two / three phases at once: the first probes are issued back to back so their latencies overlap (a control

@@ -99,8 +99,10 @@ struct FxParams {
 constexpr int kFxTlTags = 24, kFxTlIts = 64;
 #define FX_TL(tag, it)                                                                                     \
   do {                                                                                                     \
-    if (fp.timeline != nullptr && (int)blockIdx.x == fp.tl_cta && (it) >= 0 && (it) < kFxTlIts)           \
-      fp.timeline[(tag) * kFxTlIts + (it)] = clock64();                                                    \
+    if constexpr (kTimeline) {                                                                             \
+      if (fp.timeline != nullptr && (int)blockIdx.x == fp.tl_cta && (it) >= 0 && (it) < kFxTlIts)         \
+        fp.timeline[(tag) * kFxTlIts + (it)] = clock64();                                                  \
+    }                                                                                                      \
   } while (0)
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -162,10 +164,13 @@ struct FxWalk {
     return r;
   }
 };
+// 32-bit arithmetic on purpose: a 64-bit division is ~100 SASS instructions and this is inlined at every membership test
+// (it was 28 % of the grouped-head kernel's code); the host checks units * grid < 2^32 (fused_units_ok).
 __host__ __device__ __forceinline__ void fx_range(int cta, int grid, int units, int& u0, int& u1) {
-  u0 = (int)((long long)cta * units / grid);
-  u1 = (int)((long long)(cta + 1) * units / grid);
+  u0 = (int)((unsigned)cta * (unsigned)units / (unsigned)grid);
+  u1 = (int)((unsigned)(cta + 1) * (unsigned)units / (unsigned)grid);
 }
+inline bool fused_units_ok(long long units, int grid) { return units > 0 && units * (long long)(grid + 1) < (1ll << 32); }
 // Does CTA `cta` own at least one unit of the BIASED image at list position `pos` (== its group index)?
 __host__ __device__ __forceinline__ bool fx_cta_has_image(int cta, int grid, int units, int pos, int H, int tiles, int np) {
   int lo, hi;
@@ -288,6 +293,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
                    const __grid_constant__ CUtensorMap tmo0, const __grid_constant__ CUtensorMap tmo1,
                    const FxParams fp) {
   using C = Cfg<D>;
+  constexpr bool kTimeline = true;                // clock64 stamps compiled in (debug timeline of this kernel)
   const XattnParams& p = fp.x;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -929,7 +935,7 @@ cudaError_t launch_fused(const XattnParams& x, const void* mpack, int64_t mpack_
   fp.tl_cta = debug_timeline_cta();
   fp.hg = x.H;
   fp.jobs_dump = nullptr;
-  if (!fused_range_ok(x.B, x.H, fp.tiles, fp.grid)) return cudaErrorInvalidConfiguration;
+  if (!fused_range_ok(x.B, x.H, fp.tiles, fp.grid) || !fused_units_ok(fp.units, fp.grid)) return cudaErrorInvalidConfiguration;
   static bool attr_set[tc::kMaxDevices] = {false};
   if (!attr_set[tc::cur_device()]) {
     cudaError_t e = cudaFuncSetAttribute(xattn_fused_kernel<D, 77>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);

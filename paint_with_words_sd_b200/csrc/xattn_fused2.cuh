@@ -183,7 +183,10 @@ __device__ __forceinline__ bool elect_one() {     // true on exactly one lane of
   return pred != 0;
 }
 
-template <int D, int TT>
+// kTimeline = true compiles the clock64 stamps in (scripts/fused_timeline.py); the production instantiation has none of
+// them -- at the denoising loop's launch sizes every role runs its code once or twice, so kernel time tracks CODE SIZE
+// (instruction-cache misses were 20 % of the stall samples of a 197 KB build; this one is under 100 KB).
+template <int D, int TT, bool kTimeline>
 __global__ void __launch_bounds__(kThreads, 1)
 xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmm,
                     const __grid_constant__ CUtensorMap tmo0, const __grid_constant__ CUtensorMap tmo1,
@@ -215,6 +218,7 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   __shared__ float s_coef[kMaxLocal];             // g(sigma) * statistic of the CTA's local biased images
   __shared__ StatPartial s_part[16][kMaxLocal];   // [softmax warp][local biased image]
   __shared__ uint2 s_jobs[kMaxJobs];
+  __shared__ int s_expect[kMaxLocal];              // CTAs that publish a partial for each local biased image
   __shared__ unsigned s_key[16][kMaxLocal];        // max statistic: order-preserving keys of the softmax warps' partial maxima
   __shared__ signed char s_cidx[kMaxLocal][kTP];   // token -> dictionary column of the CTA's local biased images
   __shared__ int s_img0[kMaxBatch], s_widx0[kMaxBatch], s_pre;   // producer warp's own copy of the partition; early Q loads
@@ -406,12 +410,14 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   if (fp.jobs_dump != nullptr) {                              // debug: the job table as built on the device
     unsigned* d = fp.jobs_dump + (size_t)blockIdx.x * (2 + 2 * kMaxJobs);
     if (threadIdx.x == 0) { d[0] = (unsigned)njobs; d[1] = (unsigned)ns; }
+#pragma unroll 1
     for (int i = threadIdx.x; i < njobs; i += kThreads) { d[2 + 2 * i] = s_jobs[i].x; d[3 + 2 * i] = s_jobs[i].y; }
   }
   const int nu_img = p.B - nb;
   const int np = nb < nu_img ? nb : nu_img;
 
   if (blockIdx.x == 0 && p.stats_out != nullptr)            // images without a weight map report statistic 0
+#pragma unroll 1
     for (int b = threadIdx.x; b < p.B; b += kThreads)
       if (s_widx[b] < 0) p.stats_out[b] = 0.f;
 
@@ -490,6 +496,7 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         // std: fixed-order sums of the 16 warps' partials into this CTA's slot (the waiters add the slots in CTA order)
         const int lbv = s_lb[lane];
         StatPartial sp = s_part[0][lane];
+#pragma unroll 1
         for (int w2 = 1; w2 < 16; ++w2) {
           sp.sum += s_part[w2][lane].sum;
           sp.sumsq += s_part[w2][lane].sumsq;
@@ -521,20 +528,18 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     bool stats_ready = false;
     int cur_li = -1, up = -1;
     // how many CTAs publish a partial for each of my local biased images: counted now, off the critical path
-    int expect_l[kMaxLocal];
     {
       const int nl = s_nl, G = (int)gridDim.x;
-#pragma unroll
-      for (int l = 0; l < kMaxLocal; ++l) {
+#pragma unroll 1
+      for (int l = 0; l < nl && l < kMaxLocal; ++l) {
         int e = 0;
-        if (l < nl) {
-          const int pos = s_lp[l];
-          for (int c = lane; c < G; c += 32) e += fx_cta_has_image(c, G, fp.units, pos, HG, fp.tiles, np) ? 1 : 0;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
-        }
-        expect_l[l] = e;
+        const int pos = s_lp[l];
+#pragma unroll 1
+        for (int c = lane; c < G; c += 32) e += fx_cta_has_image(c, G, fp.units, pos, HG, fp.tiles, np) ? 1 : 0;
+        e = __reduce_add_sync(0xffffffffu, e);
+        if (lane == 0) s_expect[l] = e;
       }
+      __syncwarp();
     }
     const unsigned long long* sync_words = reinterpret_cast<const unsigned long long*>(p.counters + 64);
     // everything the bias operand needs besides the statistic is fetched now, not after the barrier
@@ -568,11 +573,10 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
           const int nl = s_nl;
           const int G = (int)gridDim.x;
           if (lane == 0) FX_TL(10, 0);
-#pragma unroll
-          for (int l = 0; l < kMaxLocal; ++l) {
-            if (l >= nl) break;
+#pragma unroll 1
+          for (int l = 0; l < nl && l < kMaxLocal; ++l) {
             const int bl = s_lb[l], pos = s_lp[l];
-            const unsigned expect = (unsigned)expect_l[l];
+            const unsigned expect = (unsigned)s_expect[l];
             unsigned long long word = 0;
             if (lane == 0) {
               const long long t0 = clock64();
@@ -597,7 +601,7 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
                   a += __ldcg(&pp->sum);
                   q += __ldcg(&pp->sumsq);
                 }
-#pragma unroll
+#pragma unroll 1
               for (int o = 16; o > 0; o >>= 1) {
                 a += __shfl_xor_sync(0xffffffffu, a, o);
                 q += __shfl_xor_sync(0xffffffffu, q, o);
@@ -770,7 +774,7 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         if (lane == 0 && cur_li < kMaxLocal) s_key[sw][cur_li] = kmax;
       } else {
         double a = dsum, q = dsq;
-#pragma unroll
+#pragma unroll 1
         for (int o = 16; o > 0; o >>= 1) {
           a += __shfl_xor_sync(0xffffffffu, a, o);
           q += __shfl_xor_sync(0xffffffffu, q, o);
@@ -965,7 +969,9 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     __threadfence();
     const unsigned prev = atomicAdd(p.counters + kMaxBatch, 1u);
     if (prev == gridDim.x - 1u) {
+#pragma unroll 1
       for (int b = 0; b < kMaxBatch + 1; ++b) p.counters[b] = 0u;
+#pragma unroll 1
       for (int b = 0; b < 2 * kMaxBatch; ++b) p.counters[64 + b] = 0u;      // sync words: maximum back to "-infinity", count 0
       __threadfence();
     }
@@ -997,7 +1003,7 @@ inline bool make_tmap_qfull(CUtensorMap* m, const void* base, int C, int N, int 
 // (job table in shared memory); the C ABI halves the images per launch until it does.
 inline bool fused2_fits(int B, int hg, int tiles, int grid) {
   const long long units = (long long)B * hg * tiles;
-  return fused_range_ok(B, hg, tiles, grid) && (units + grid - 1) / grid + 1 <= kMaxUnits;
+  return fused_range_ok(B, hg, tiles, grid) && fused_units_ok(units, grid) && (units + grid - 1) / grid + 1 <= kMaxUnits;
 }
 
 template <int D>
@@ -1028,9 +1034,11 @@ cudaError_t launch_fused2(const XattnParams& x, const void* mpack, int64_t mpack
   if (!fused2_fits(x.B, fp.hg, fp.tiles, fp.grid)) return cudaErrorInvalidConfiguration;
   static bool attr_set[tc::kMaxDevices] = {false};
   if (!attr_set[tc::cur_device()]) {
-    cudaError_t e = cudaFuncSetAttribute(xattn_fused2_kernel<D, 77>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(xattn_fused2_kernel<D, 77, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(xattn_fused2_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+      e = cudaFuncSetAttribute(xattn_fused2_kernel<D, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(xattn_fused2_kernel<D, 77, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) return e;
     attr_set[tc::cur_device()] = true;
   }
@@ -1045,8 +1053,9 @@ cudaError_t launch_fused2(const XattnParams& x, const void* mpack, int64_t mpack
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (x.T == 77) return cudaLaunchKernelEx(&cfg, xattn_fused2_kernel<D, 77>, tq, tm, to0, to1, fp);
-  return cudaLaunchKernelEx(&cfg, xattn_fused2_kernel<D, 0>, tq, tm, to0, to1, fp);
+  if (x.T == 77 && fp.timeline != nullptr) return cudaLaunchKernelEx(&cfg, xattn_fused2_kernel<D, 77, true>, tq, tm, to0, to1, fp);
+  if (x.T == 77) return cudaLaunchKernelEx(&cfg, xattn_fused2_kernel<D, 77, false>, tq, tm, to0, to1, fp);
+  return cudaLaunchKernelEx(&cfg, xattn_fused2_kernel<D, 0, false>, tq, tm, to0, to1, fp);
 }
 
 // Host replay of the job lists (test infrastructure): out[job] = {cta, i, kind, m, b, h, tile, biased, li, gi, up, ul,
