@@ -205,14 +205,36 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU reference arm (oracle port of the reference loop)
 # ------------------------------------------------------------------------------------------------
+def host_threads() -> int:
+    """Threads the CPU arm may really use: the affinity mask, capped by the cgroup CPU quota (a container that shows 128
+    logical CPUs but is allowed 16 cores' worth of time runs a 128-thread GEMM far slower than a 16-thread one)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:                       # cgroup v2: "<quota> <period>" or "max <period>"
+            quota, period = f.read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(math.ceil(int(quota) / int(period)))))
+    except Exception:
+        try:
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f:
+                quota = int(f.read())
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+                period = int(f.read())
+            if quota > 0:
+                n = min(n, max(1, int(math.ceil(quota / period))))
+        except Exception:
+            pass
+    return max(1, n)
+
+
 def cpu_reference(max_timed_steps: int, warmup: int, budget_s: float):
     """Timed oracle loop on the host cores: same UNet weights (seed 0, fp32), same conditioning, same schedule."""
     from oracle import loop as oracle_loop
-    # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses every host core it can, whatever launched it
-    try:
-        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
-    except Exception:
-        torch.set_num_threads(max(1, os.cpu_count() or 1))
+    # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses every host core it CAN use, whatever launched it
+    torch.set_num_threads(host_threads())
     torch.manual_seed(0)
     unet = build_unet(UNetConfig.sd15(), seed=0, dtype=torch.float32, device="cpu")
     oracle_loop.patch_with_oracle(unet)
