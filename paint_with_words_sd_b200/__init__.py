@@ -10,8 +10,8 @@ from .conditioning import (  # noqa: F401
     _image_context_seperator, _img_importance_flatten, _tokens_img_attention_weight, always_round,
 )
 from .pipeline import (  # noqa: F401
-    PwWSampler, paint_with_words, paint_with_words_inpaint, preprocess, prepare_mask_and_masked_image,
-    pww_load_tools,
+    PaintWithWord_StableDiffusionInpaintPipeline, PaintWithWord_StableDiffusionPipeline, PwWSampler, paint_with_words,
+    paint_with_words_inpaint, preprocess, prepare_mask_and_masked_image, pww_load_tools,
 )
 from .scheduler import LMSDiscreteScheduler  # noqa: F401
 from .weight_function import UnsupportedWeightFunction, WeightFunction, probe_weight_function  # noqa: F401

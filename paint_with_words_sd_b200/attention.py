@@ -111,6 +111,10 @@ def resolve_weight_map(context: dict, n: int, device):
     except KeyError:
         w = context[_ORIG_KEY]
         if isinstance(w, int):
+            if context.get("ORIG_FALLBACK_DROPPED"):
+                raise NotImplementedError(
+                    f"no CROSS_ATTENTION_WEIGHT_{n} in a multi-image context: the ORIG-map fallback (paint_with_words.py:97-103) "
+                    "is a single-image path; use sizes divisible by 64 or one image per sampler")
             return 0
         w = expand_orig_weight_map(w.detach().to("cpu", torch.float32), n).to(device)
         context[weight_key(n)] = w
@@ -254,14 +258,16 @@ def self_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int
 
 
 def _fused_weight(module, attr: str, names) -> torch.Tensor:
-    """Row-concatenated projection weights (to_q|to_k|to_v or to_k|to_v), built once per module (inference weights
-    are static): one GEMM instead of two or three."""
-    w = getattr(module, attr, None)
-    ref = getattr(module, names[0]).weight
-    if w is None or w.device != ref.device or w.dtype != ref.dtype:
-        w = torch.cat([getattr(module, n).weight for n in names], 0).detach().contiguous()
-        object.__setattr__(module, attr, w)
-    return w
+    """Row-concatenated projection weights (to_q|to_k|to_v or to_k|to_v), built once per module: one GEMM instead of
+    two or three.  The cache is keyed on the parameters' storage and version counters, so an in-place update of the
+    weights (load_state_dict, a broadcast into the module after a first forward) rebuilds it."""
+    params = [getattr(module, n).weight for n in names]
+    key = tuple((p.data_ptr(), p._version, p.dtype, p.device) for p in params)
+    hit = getattr(module, attr, None)
+    if hit is None or hit[0] != key:
+        hit = (key, torch.cat(params, 0).detach().contiguous())
+        object.__setattr__(module, attr, hit)
+    return hit[1]
 
 
 def refresh_kv_cache(context: dict) -> None:

@@ -180,7 +180,9 @@ class PwWSampler:
                 continue
             vals = [c[key] for c in conds]
             if key == "CROSS_ATTENTION_WEIGHT_ORIG":
-                ctx[key] = vals[0] if m == 1 else 0   # ORIG fallback is a single-image path
+                ctx[key] = vals[0] if m == 1 else 0   # ORIG fallback is a single-image path ...
+                if m > 1 and any(isinstance(v, torch.Tensor) for v in vals):
+                    ctx["ORIG_FALLBACK_DROPPED"] = True   # ... and a level that would need it raises instead of losing its bias
                 continue
             if all(isinstance(v, torch.Tensor) for v in vals):
                 dense = torch.stack([v.detach().to("cpu", torch.float32) for v in vals], 0).contiguous()
@@ -448,3 +450,92 @@ def paint_with_words_inpaint(
     if return_latents:
         return latents
     return _pil_from_latents(vae, latents)[0]
+
+
+# ---------------------------------------------------------------------------------------------
+# pipeline classes (paint_with_words.py:513-842, paint_with_words_inpaint.py:273-575): API surface only
+# ---------------------------------------------------------------------------------------------
+class PipelineOutput:
+    """Stand-in for diffusers' StableDiffusionPipelineOutput: `.images`, `.nsfw_content_detected`."""
+
+    def __init__(self, images, nsfw_content_detected=False):
+        self.images, self.nsfw_content_detected = images, nsfw_content_detected
+
+
+class PaintWithWord_StableDiffusionPipeline:
+    """Same constructor / `from_pretrained` / `plugin_cross_attention` / `__call__` surface as the reference class
+    (paint_with_words.py:513-842); the work is `paint_with_words()` above (one `PwWSampler`).  Like the reference class
+    it always uses its own LMS scheduler (paint_with_words.py:534-539) and has no regional blur (:574)."""
+
+    def __init__(self, vae, text_encoder, tokenizer, unet, scheduler=None, safety_checker=None, feature_extractor=None,
+                 requires_safety_checker: bool = False):
+        self.vae, self.text_encoder, self.tokenizer, self.unet = vae, text_encoder, tokenizer, unet
+        self.safety_checker, self.feature_extractor = safety_checker, feature_extractor
+        self.scheduler = LMSDiscreteScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                                              num_train_timesteps=1000)
+        self.plugin_cross_attention()
+
+    @classmethod
+    def from_pretrained(cls, save_dir, device: str = "cuda:0", **kwargs):
+        vae, unet, text_encoder, tokenizer, scheduler = pww_load_tools(device, local_model_path=save_dir)
+        return cls(vae=vae, text_encoder=text_encoder, tokenizer=tokenizer, unet=unet, scheduler=scheduler)
+
+    def plugin_cross_attention(self):
+        """paint_with_words.py:556-559."""
+        return _attention.patch_unet(self.unet)
+
+    @property
+    def device(self):
+        return next(iter(self.unet.parameters())).device
+
+    def _run(self, fn, prompt, color_map_image, color_context, weight_function, num_inference_steps, guidance_scale,
+             negative_prompt, seed, output_type, return_dict, callback, callback_steps, **extra):
+        if isinstance(prompt, (list, tuple)):
+            if len(prompt) != 1:
+                raise ValueError("the Paint-with-Words pipelines take one prompt per call (batch size 1, paint_with_words.py:445)")
+            prompt = prompt[0]
+        if isinstance(negative_prompt, (list, tuple)):
+            negative_prompt = negative_prompt[0]
+        tools = (self.vae, self.unet, self.text_encoder, self.tokenizer, self.scheduler)
+        latents = fn(color_context=color_context, color_map_image=color_map_image, input_prompt=prompt,
+                     num_inference_steps=num_inference_steps, guidance_scale=guidance_scale, seed=seed,
+                     device=str(self.device), weight_function=weight_function, preloaded_utils=tools,
+                     unconditional_input_prompt=negative_prompt or "", return_latents=True, **extra)
+        if callback is not None:
+            callback(num_inference_steps - 1, int(self.scheduler.timesteps[-1]), latents)
+        if output_type == "latent":
+            images = latents
+        else:
+            images = _pil_from_latents(self.vae, latents)
+            if output_type != "pil":
+                images = np.stack([np.asarray(im, dtype=np.float32) / 255.0 for im in images])
+        return PipelineOutput(images, False) if return_dict else (images, False)
+
+    @torch.no_grad()
+    def __call__(self, prompt, color_map_image=None, color_context={}, weight_function: Callable = default_weight_function,
+                 height=None, width=None, num_inference_steps: int = 30, guidance_scale: float = 7.5, negative_prompt="",
+                 num_images_per_prompt: int = 1, eta: float = 0.5, seed: int = 0, generator=None, image=None, latents=None,
+                 output_type: str = "pil", return_dict: bool = True, callback=None, callback_steps: int = 1):
+        extra = {} if image is None else {"init_image": image, "strength": eta}
+        return self._run(paint_with_words, prompt, color_map_image, dict(color_context), weight_function,
+                         num_inference_steps, guidance_scale, negative_prompt, seed, output_type, return_dict, callback,
+                         callback_steps, **extra)
+
+
+class PaintWithWord_StableDiffusionInpaintPipeline(PaintWithWord_StableDiffusionPipeline):
+    """paint_with_words_inpaint.py:273-575: `__call__(prompt, image, mask_image, color_map_image, color_context, ...)`."""
+
+    @classmethod
+    def from_pretrained(cls, save_dir, device: str = "cuda:0", **kwargs):
+        vae, unet, text_encoder, tokenizer, scheduler = pww_load_tools(device, local_model_path=save_dir)
+        return cls(vae=vae, text_encoder=text_encoder, tokenizer=tokenizer, unet=unet, scheduler=scheduler)
+
+    @torch.no_grad()
+    def __call__(self, prompt, image=None, mask_image=None, color_map_image=None, color_context={},
+                 weight_function: Callable = default_weight_function, height=None, width=None,
+                 num_inference_steps: int = 30, guidance_scale: float = 7.5, negative_prompt="",
+                 num_images_per_prompt: int = 1, eta: float = 1.0, seed: int = 0, generator=None, latents=None,
+                 output_type: str = "pil", return_dict: bool = True, callback=None, callback_steps: int = 1):
+        return self._run(paint_with_words_inpaint, prompt, color_map_image, dict(color_context), weight_function,
+                         num_inference_steps, guidance_scale, negative_prompt, seed, output_type, return_dict, callback,
+                         callback_steps, mask_image=mask_image, init_image=image, strength=eta)

@@ -119,6 +119,8 @@ def probe_weight_function(f: Callable, sigma=1.0) -> ProbedFunction:
                 raise UnsupportedWeightFunction(
                     "weight_function is not of the form G(sigma) * w * stat(qk); cannot be fused")
             res = ProbedFunction(STAT_MAX if use_max else STAT_STD)
+    while len(_PROBE_CACHE) >= 64:            # the reference-style loop builds a fresh uncond lambda every step: keep it bounded
+        _PROBE_CACHE.pop(next(iter(_PROBE_CACHE)))
     _PROBE_CACHE[id(f)] = (f, res)
     return res
 

@@ -15,14 +15,20 @@ from paint_with_words_sd_b200 import attention as A  # noqa: E402
 
 torch.manual_seed(0)
 dev = "cuda"
-B, N, H, D, T = 2, 1024, 8, 40, 77
+B, N, H, D, T = 4, 1024, 8, 40, 77      # 4 images: with PWW_DEBUG_GRID=6 every CTA runs ring mode over ~10 units
 q = (torch.randn(B, N, H * D) * 0.5).half().to(dev)
 k = (torch.randn(B, T, H * D) * 0.5).half().to(dev)
 v = (torch.randn(B, T, H * D) * 0.5).half().to(dev)
-w = torch.zeros(1, N, T)
-w[0, :, 3] = (torch.rand(N) > 0.5).float() * 1.5
-w[0, :, 9] = (torch.rand(N) > 0.5).float() * 0.7
-idx = torch.tensor([0, -1], dtype=torch.int32, device=dev)
+w = torch.zeros(2, N, T)
+for i in range(2):
+    w[i, :, 3 + i] = (torch.rand(N) > 0.5).float() * 1.5
+    w[i, :, 9 + i] = (torch.rand(N) > 0.5).float() * 0.7
+idx = torch.tensor([0, -1, 1, -1], dtype=torch.int32, device=dev)
+if os.environ.get("PWW_DEBUG_GRID"):
+    import ctypes
+    L = _native.lib()
+    L.pww_debug_set_fused_grid.argtypes = [ctypes.c_int]
+    L.pww_debug_set_fused_grid(int(os.environ["PWW_DEBUG_GRID"]))
 gs = torch.tensor([0.4 * math.log(8.0)], dtype=torch.float32, device=dev)
 out = A.cross_attention(q, k, v, H, D ** -0.5, w.to(dev), idx, _native.PWW_STAT_MAX, gs)
 torch.cuda.synchronize()

@@ -163,3 +163,60 @@ def test_attn_processor_hook_matches_class_patch():
         e = inj_forward(attn, x, ctx)                        # tensor context: no bias
     assert torch.equal(a, b) and a.shape == x.shape and torch.isfinite(c).all()
     assert not torch.equal(a, e)                             # the bias did something
+
+
+def test_pipeline_classes_match_the_functional_api():
+    """paint_with_words.py:513-842 / paint_with_words_inpaint.py:273-575: the pipeline classes are a thin surface over the
+    functional API -- same latents for the same inputs."""
+    s = SETTINGS["aurora"]
+    tools = P.pww_load_tools("cuda:0", hf_model_path="synthetic:tiny")
+    try:
+        vae, unet, enc, tok, sch = tools
+        pipe = P.PaintWithWord_StableDiffusionPipeline(vae=vae, text_encoder=enc, tokenizer=tok, unet=unet, scheduler=sch)
+        out = pipe(s["prompt"], color_map_image=color_map_image("aurora", 128), color_context=dict(s["ctx"]),
+                   weight_function=WF, num_inference_steps=3, seed=3, output_type="latent")
+        ref = P.paint_with_words(color_context=dict(s["ctx"]), color_map_image=color_map_image("aurora", 128),
+                                 input_prompt=s["prompt"], num_inference_steps=3, seed=3, device="cuda:0",
+                                 weight_function=WF, preloaded_utils=(vae, unet, enc, tok, pipe.scheduler), return_latents=True)
+        assert torch.equal(out.images, ref) and out.nsfw_content_detected is False
+        img = pipe(s["prompt"], color_map_image=color_map_image("aurora", 128), color_context=dict(s["ctx"]),
+                   weight_function=WF, num_inference_steps=2).images[0]
+        assert img.size == (128, 128)
+        unet9 = build_unet(UNetConfig.tiny(in_channels=9), seed=0, dtype=torch.float16, device="cuda")
+        ipipe = P.PaintWithWord_StableDiffusionInpaintPipeline(vae=vae, text_encoder=enc, tokenizer=tok, unet=unet9)
+        res = ipipe(s["prompt"], image=color_map_image("aurora", 128), mask_image=moon_mask_image(128),
+                    color_map_image=color_map_image("aurora", 128), color_context=dict(s["ctx"]), weight_function=WF,
+                    num_inference_steps=2, return_dict=False)
+        assert res[0][0].size == (128, 128) and res[1] is False
+    finally:
+        P.unpatch_all()
+
+
+def test_sampler_feeds_modules_their_own_dtype_and_follows_weight_updates():
+    """the reference runs under torch.autocast; a diffusers fp16 UNet does not cast its input itself, so the
+    sampler must hand it fp16 (a module that asserts its input dtype stands in for one).  And the fused projection
+    weights the shim caches per module must follow an in-place weight update."""
+    cfg = UNetConfig.tiny()
+    unet = build_unet(cfg, seed=0, dtype=torch.float16, device="cuda")
+
+    class Strict(torch.nn.Module):
+        def __init__(self, inner):
+            super().__init__()
+            self.inner, self.in_channels = inner, inner.in_channels
+
+        def forward(self, sample, t, encoder_hidden_states=None):
+            assert sample.dtype == torch.float16, sample.dtype
+            return self.inner(sample, t, encoder_hidden_states=encoder_hidden_states)
+
+    cond, uncond, sch, lat = _setup(cfg, 128, 3, "cuda")
+    try:
+        P.patch_unet(unet)
+        a = PwWSampler(Strict(unet), sch, [cond], [uncond], lat.cuda(), WF, 7.5, use_graph=False).run().clone()
+        with torch.no_grad():
+            for m in attention_modules(unet):
+                m.to_q.weight.mul_(0.5)                       # in place: same storage, new version
+        cond, uncond, sch, lat = _setup(cfg, 128, 3, "cuda")
+        b = PwWSampler(Strict(unet), sch, [cond], [uncond], lat.cuda(), WF, 7.5, use_graph=False).run().clone()
+    finally:
+        P.unpatch_all()
+    assert torch.isfinite(a).all() and torch.isfinite(b).all() and not torch.equal(a, b)
