@@ -131,11 +131,12 @@ def _rows(t: torch.Tensor) -> torch.Tensor:
 
 
 # "fused": one launch (statistic + bias + softmax + PV, packed maps); "dense": round-1 pair of launches on the dense fp32
-# map; "auto" (default): the one-launch kernel where it is the faster of the two on this hardware -- head dim 40, the
-# grouped-head kernel of csrc/xattn_fused2.cuh (N = 4096 level of SD1.5: 18 vs 22 us at the cond+uncond launch, 48 vs 67 us
-# at 16 images) -- and the pair elsewhere (head dims 64 / 80 / 160 still run the per-head one-launch kernel, which the pair
-# beats: profiles/r02_microbench_sd15.jsonl, ..._sd21.jsonl).  Maps that cannot be packed (> 10 distinct columns) always
-# take the dense pair.
+# map; "auto" (default): the one-launch kernel where it is at least as fast as the pair on this hardware -- head dims 40 /
+# 80 / 160, i.e. every level of SD1.5, where the grouped-head kernel of csrc/xattn_fused2.cuh runs (N = 4096: 15.8 vs
+# 22.5 us at the cond+uncond launch, 45 vs 65 us at 16 images; N = 1024: 15.5 vs 16.6 / 27.7 vs 28.3; N = 256: 16.7 vs
+# 17.3 / 18.9 vs 22.5; profiles/r02_microbench_sd15_final.jsonl) -- and the pair at head dim 64 (SD2.1), which still has
+# only the per-head one-launch kernel (slower than the pair: profiles/r02_microbench_sd21.jsonl).  Maps that cannot be
+# packed (> 10 distinct columns) always take the dense pair.
 XATTN_IMPL = "auto"
 
 
@@ -166,7 +167,7 @@ def cross_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: in
                 wmap = wmap.unsqueeze(0)
             if wmap.shape[1] != N or wmap.shape[2] != T:
                 raise ValueError(f"weight map shape {tuple(wmap.shape)} does not match N={N}, T={T}")
-        impl = XATTN_IMPL if XATTN_IMPL != "auto" else ("fused" if D == 40 else "dense")
+        impl = XATTN_IMPL if XATTN_IMPL != "auto" else ("fused" if D in (40, 80, 160) else "dense")
         if impl == "dense" and biased and wmap is None:
             impl = "fused"                          # only the packed form was given
         if biased and packed is None and impl == "fused":

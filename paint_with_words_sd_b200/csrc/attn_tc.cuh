@@ -162,15 +162,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const Params p) {
   // the row sum; padded keys have P = 0, so every row may carry the 1) followed by zeros.
   {
     constexpr int kpad = (C::DP - D) / 8, vpad = (C::DPV - D) / 8;      // 16-byte chunks
-    for (int idx = threadIdx.x; idx < C::NK * C::BN * kpad; idx += kThreads) {
-      const int st = idx / (C::BN * kpad), rem = idx % (C::BN * kpad), r = rem / kpad, c = D / 8 + rem % kpad;
-      *reinterpret_cast<uint4*>(smem_gen + C::OFF_K + st * C::KSTAGE + (c / 8) * C::KATOM + r * 128 + (((c % 8) ^ (r & 7)) << 4)) =
-          make_uint4(0, 0, 0, 0);
+    if constexpr (kpad > 0) {
+      for (int idx = threadIdx.x; idx < C::NK * C::BN * kpad; idx += kThreads) {
+        const int st = idx / (C::BN * kpad), rem = idx % (C::BN * kpad), r = rem / kpad, c = D / 8 + rem % kpad;
+        *reinterpret_cast<uint4*>(smem_gen + C::OFF_K + st * C::KSTAGE + (c / 8) * C::KATOM + r * 128 + (((c % 8) ^ (r & 7)) << 4)) =
+            make_uint4(0, 0, 0, 0);
+      }
     }
-    for (int idx = threadIdx.x; idx < C::NV * C::BN * vpad; idx += kThreads) {
-      const int st = idx / (C::BN * vpad), rem = idx % (C::BN * vpad), r = rem / vpad, c = D / 8 + rem % vpad;
-      *reinterpret_cast<uint4*>(smem_gen + C::OFF_V + st * C::VSTAGE + (c / 8) * C::KATOM + r * 128 + (((c % 8) ^ (r & 7)) << 4)) =
-          make_uint4((C::ONES && c == D / 8) ? 0x00003C00u : 0u, 0, 0, 0);
+    if constexpr (vpad > 0) {
+      for (int idx = threadIdx.x; idx < C::NV * C::BN * vpad; idx += kThreads) {
+        const int st = idx / (C::BN * vpad), rem = idx % (C::BN * vpad), r = rem / vpad, c = D / 8 + rem % vpad;
+        *reinterpret_cast<uint4*>(smem_gen + C::OFF_V + st * C::VSTAGE + (c / 8) * C::KATOM + r * 128 + (((c % 8) ^ (r & 7)) << 4)) =
+            make_uint4((C::ONES && c == D / 8) ? 0x00003C00u : 0u, 0, 0, 0);
+      }
     }
     ptx::fence_proxy_async_smem();
   }

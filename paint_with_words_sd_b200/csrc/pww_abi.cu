@@ -189,8 +189,10 @@ int pww_xattn_fused_f16(const void* q, const void* k, const void* v, void* out, 
   cudaStream_t s = (cudaStream_t)stream;
   // image b is biased iff it has a packed map: with mpack == NULL every index is -1 (the kernel reads wmap_index)
   int chunk = pww::fx::kMaxBatch;                                  // images per launch
-  if (D == 40 && pww::fx::fused_variant() == 0) {                  // grouped-head kernel: job table of <= 64 units per CTA
-    const int tiles = pww::ceil_div(N, pww::fx::kBM), hg = pww::ceil_div(H, pww::fx2::Cfg2<40>::G);
+  const bool grouped = (D == 40 || D == 80 || D == 160) && pww::fx::fused_variant() == 0;
+  if (grouped) {                                                   // grouped-head kernel: job table of <= 64 units per CTA
+    const int tiles = pww::ceil_div(N, pww::fx::kBM);
+    const int hg = pww::ceil_div(H, D == 40 ? pww::fx2::Cfg2<40>::G : 1);
     while (chunk > 1) {
       const int cb = B < chunk ? B : chunk;
       if (pww::fx2::fused2_fits(cb, hg, tiles, pww::fx::fused_grid(cb * hg * tiles))) break;
@@ -217,11 +219,13 @@ int pww_xattn_fused_f16(const void* q, const void* k, const void* v, void* out, 
     c.wmap = mpack ? (const float*)mp : nullptr;                   // non-null marks "maps present" for the kernel
     cudaError_t e = cudaErrorInvalidValue;
     switch (D) {
-      case 40: e = pww::fx::fused_variant() == 1 ? pww::fx::launch_fused<40>(c, mp, mpack_batch_stride, Bw, ci, s)
-                                                 : pww::fx2::launch_fused2<40>(c, mp, mpack_batch_stride, Bw, ci, s); break;
+      case 40: e = grouped ? pww::fx2::launch_fused2<40>(c, mp, mpack_batch_stride, Bw, ci, s)
+                           : pww::fx::launch_fused<40>(c, mp, mpack_batch_stride, Bw, ci, s); break;
       case 64: e = pww::fx::launch_fused<64>(c, mp, mpack_batch_stride, Bw, ci, s); break;
-      case 80: e = pww::fx::launch_fused<80>(c, mp, mpack_batch_stride, Bw, ci, s); break;
-      case 160: e = pww::fx::launch_fused<160>(c, mp, mpack_batch_stride, Bw, ci, s); break;
+      case 80: e = grouped ? pww::fx2::launch_fused2<80>(c, mp, mpack_batch_stride, Bw, ci, s)
+                           : pww::fx::launch_fused<80>(c, mp, mpack_batch_stride, Bw, ci, s); break;
+      case 160: e = grouped ? pww::fx2::launch_fused2<160>(c, mp, mpack_batch_stride, Bw, ci, s)
+                            : pww::fx::launch_fused<160>(c, mp, mpack_batch_stride, Bw, ci, s); break;
     }
     if (e == cudaErrorInvalidConfiguration) return PWW_ERR_UNSUPPORTED;
     if (e != cudaSuccess) return cuda_fail(e);

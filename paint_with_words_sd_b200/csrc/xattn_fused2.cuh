@@ -31,41 +31,47 @@ using namespace fx;   // unit walk, helpers and constants shared with the per-he
 
 template <int D>
 struct Cfg2 {
-  static_assert(D == 40, "the grouped-head kernel is built for head dim 40");
+  static_assert(D == 40 || D == 80 || D == 160, "the grouped-head kernel is built for the SD1.5 head dims");
 #ifndef PWW_FX2_G
 #define PWW_FX2_G 2
 #endif
-  static constexpr int G = PWW_FX2_G;               // heads per unit (2: 80 columns inside 2 atoms; 4: 160 columns inside 3)
-  static_assert(G == 2 || G == 4, "heads per unit");
-  static constexpr int NAQ = (G == 4) ? 3 : 2;      // 64-column atoms that cover the unit's G * D columns wherever they start
+  // heads per unit: 2 x 40 columns at head dim 40 (the unit's 80 columns sit inside 2 atoms wherever they start); one
+  // head at 80 (2 atoms) and at 160 (3 atoms)
+  static constexpr int G = (D == 40) ? PWW_FX2_G : 1;
+  static_assert(G == 1 || G == 2 || G == 4, "heads per unit");
+  static constexpr int NAQ = (G * D > 80) ? 3 : 2;  // 64-column atoms that cover the unit's G * D columns wherever they start
+  static constexpr int NA = (D + 63) / 64;          // 64-column atoms of a head's K / V tile
   static constexpr int DP = (D + 15) / 16 * 16;
-  static constexpr int KSTEPS = DP / 16;            // 16-column blocks per head: 3 (a head starts 0 or 8 columns into its first block)
-  static constexpr bool ONES = true;                // row sums ride on the P.V UMMA (spare V column = 1.0)
-  static constexpr int DPV = (D + 16) / 16 * 16;    // UMMA N of P.V: 48
-  static constexpr int NS = 4;                      // score slots (80 fp32 columns each; P overwrites the S it came from)
-  static constexpr int NO = 4;                      // output accumulators (48 columns each)
+  static constexpr int KSTEPS = DP / 16;            // 16-column blocks per head (at 40: 3, the head starts 0 or 8 columns into its first block)
+  static constexpr bool ONES = (D == 40 || D == 80);            // row sums ride on the P.V UMMA (spare V column = 1.0)
+  static constexpr int DPV = ONES ? (D + 16) / 16 * 16 : DP;    // UMMA N of P.V: 48, 96, 160
+  static constexpr int NS = (D <= 80) ? 4 : 2;      // score slots (80 fp32 columns each; P overwrites the S it came from)
+  static constexpr int NO = (D == 40) ? 4 : 2;      // output accumulators
   static constexpr uint32_t O_STRIDE = DPV;
   __host__ __device__ static constexpr uint32_t col_s(int slot) { return (uint32_t)slot * 80u; }
   __host__ __device__ static constexpr uint32_t col_o(int os) { return (uint32_t)NS * 80u + (uint32_t)os * O_STRIDE; }
   static_assert(NS * 80 + NO * DPV <= 512, "TMEM budget");
-  static constexpr int NQ = 2;                      // Q ring: unit passes in flight (or resident units)
-  static constexpr int NK = 3;                      // K ring: jobs in flight
-  static constexpr int NV = 3;                      // V ring: main jobs in flight
+  static constexpr int NQ = (D == 160) ? 1 : 2;     // Q ring: unit passes in flight (or resident units)
+  static constexpr int NK = (D == 40) ? 3 : 2;      // K ring: jobs in flight
+  static constexpr int NV = (D == 40) ? 3 : (D == 80 ? 2 : 1);  // V ring: main jobs in flight
   static constexpr uint32_t QBYTES = NAQ * kQAtom;
-  static constexpr uint32_t QSTAGE = QBYTES + kMAtom;           // 3 Q atoms | packed-map atom of the row tile
-  static constexpr uint32_t KSTAGE = kKAtom, VSTAGE = kKAtom;
-  static constexpr int C0 = 24, C1 = D - C0;        // output columns of the two threads of a row (multiples of 8)
-  static constexpr int EPI_W = C0;
-  static constexpr int EPI_NPASS = 1;
+  static constexpr uint32_t QSTAGE = QBYTES + kMAtom;           // Q atoms | packed-map atom of the row tile
+  static constexpr uint32_t KSTAGE = NA * kKAtom, VSTAGE = NA * kKAtom;
+  // output columns of the two threads of a row; every piece is a multiple of 8 columns (16-byte TMA boxes)
+  static constexpr int C0 = (D == 40) ? 24 : D / 2;
+  static constexpr int C1 = D - C0;
+  static constexpr int EPI_W = (D == 160) ? 40 : C0;            // columns per epilogue pass (staging row width)
+  static constexpr int EPI_NPASS = (D == 160) ? 2 : 1;
   static constexpr uint32_t STG_WARP = 32 * EPI_W * 2;
   static constexpr uint32_t OFF_K = NQ * QSTAGE;
   static constexpr uint32_t OFF_V = OFF_K + NK * KSTAGE;
   static constexpr uint32_t OFF_COEF = OFF_V + NV * VSTAGE;     // 2 B-operand tiles [80 x 32 fp16], 64-byte-swizzled rows
   static constexpr uint32_t OFF_STG = OFF_COEF + 2 * kCoefTile;
-  static constexpr uint32_t OFF_XCHG = OFF_STG + 16 * STG_WARP; // [group][buf][half][128] fp32 row maxima
+  static constexpr uint32_t OFF_XCHG = OFF_STG + 16 * STG_WARP; // [group][buf][half][128] fp32 row maxima, then row sums
   static constexpr uint32_t OFF_BAR = OFF_XCHG + 2 * 2 * 2 * 128 * 4 * 2;
   static constexpr uint32_t SMEM = OFF_BAR + 512 + 1024;        // + alignment slack
-  static_assert(SMEM <= 232448 - 8192, "shared memory budget (dynamic + static tables incl. the 4 KB job table)");
+  static_assert(SMEM + 7680 <= 232448, "shared memory budget (dynamic + ~7.3 KB of static tables incl. the 4 KB job table)");
+  static_assert(16 * STG_WARP >= 64 * 16, "the job-table scratch (kMaxUnits x 16 bytes) lives in the staging area");
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -358,21 +364,29 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     s_part[i / kMaxLocal][i % kMaxLocal] = sp;
     s_key[i / kMaxLocal][i % kMaxLocal] = 0u;      // key 0 is below every real number
   }
-  // K / V ring stages, once: zero rows T..79 (the per-job copies never touch them); V chunk column 5 = [1.0, 0 x 7] for real
-  // tokens -- the spare column that makes accumulator column D of the P.V UMMA the row sum -- and zero for padded ones.
-  for (int idx = threadIdx.x; idx < C::NK * (kTP - T) * 6; idx += kThreads) {
-    const int stz = idx / ((kTP - T) * 6), rem = idx - stz * ((kTP - T) * 6);
-    const int t = T + rem / 6, ch = rem % 6;
-    *reinterpret_cast<uint4*>(smem_gen + C::OFF_K + stz * C::KSTAGE + t * 128 + ((ch ^ (t & 7)) << 4)) = make_uint4(0, 0, 0, 0);
-  }
-  for (int idx = threadIdx.x; idx < C::NV * kTP; idx += kThreads) {
-    const int stz = idx / kTP, t = idx - stz * kTP;
-    unsigned char* vrow = smem_gen + C::OFF_V + stz * C::VSTAGE + t * 128;
-    if (t >= T) {
-#pragma unroll
-      for (int ch = 0; ch < 5; ++ch) *reinterpret_cast<uint4*>(vrow + ((ch ^ (t & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+  // K / V ring stages, once: zero rows T..79 (the per-job copies never touch them); V columns D .. DPV-1 = [1.0, 0 ...] for
+  // real tokens -- the spare column that makes accumulator column D of the P.V UMMA the row sum -- and zero for padded ones.
+  {
+    constexpr int kch = C::DP / 8, vch = C::DPV / 8;           // 16-byte chunks the UMMAs read per row
+    for (int idx = threadIdx.x; idx < C::NK * (kTP - T) * kch; idx += kThreads) {
+      const int stz = idx / ((kTP - T) * kch), rem = idx - stz * ((kTP - T) * kch);
+      const int t = T + rem / kch, ch = rem % kch;
+      *reinterpret_cast<uint4*>(smem_gen + C::OFF_K + stz * C::KSTAGE + (ch >> 3) * kKAtom + t * 128 + (((ch & 7) ^ (t & 7)) << 4)) =
+          make_uint4(0, 0, 0, 0);
     }
-    *reinterpret_cast<uint4*>(vrow + ((5 ^ (t & 7)) << 4)) = make_uint4(t < T ? 0x00003C00u : 0u, 0, 0, 0);
+    for (int idx = threadIdx.x; idx < C::NV * kTP; idx += kThreads) {
+      const int stz = idx / kTP, t = idx - stz * kTP;
+      unsigned char* vrow = smem_gen + C::OFF_V + stz * C::VSTAGE + t * 128;
+      if (t >= T) {
+#pragma unroll 1
+        for (int ch = 0; ch < D / 8; ++ch)
+          *reinterpret_cast<uint4*>(vrow + (ch >> 3) * kKAtom + (((ch & 7) ^ (t & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll 1
+      for (int ch = D / 8; ch < vch; ++ch)
+        *reinterpret_cast<uint4*>(vrow + (ch >> 3) * kKAtom + (((ch & 7) ^ (t & 7)) << 4)) =
+            make_uint4((C::ONES && ch == D / 8 && t < T) ? 0x00003C00u : 0u, 0, 0, 0);
+    }
   }
   ptx::fence_proxy_async_smem();                   // generic-proxy writes above -> visible to the UMMAs (async proxy)
   if (warp == 3 && lane == 0) {
@@ -434,7 +448,10 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         const uint32_t drow = tile + t * 128;
         const int x7 = t & 7;
 #pragma unroll
-        for (int ch = 0; ch < 5; ++ch) cp_async16(drow + (((ch + shift) ^ x7) << 4), srow + ch, 16u);
+        for (int ch = 0; ch < D / 8; ++ch) {             // chunk ch -> atom (ch + shift) / 8, chunk column (ch + shift) % 8
+          const int cc = ch + shift;
+          cp_async16(drow + (cc >> 3) * kKAtom + (((cc & 7) ^ x7) << 4), srow + ch, 16u);
+        }
         if (zc >= 0) cp_async16(drow + ((zc ^ x7) << 4), srow, 0u);
       }
     }
@@ -474,8 +491,8 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       //      8 columns into its first 16-column block); the chunk column the shift leaves free is zeroed ----
       const int st = i % C::NK;
       ptx::mbar_wait(BAR(B_KEMPTY + st), (uint32_t)(((i / C::NK) & 1) ^ 1));
-      const int sh = ((h * D) % 16) ? 1 : 0;
-      copy_kv(smem0 + C::OFF_K + st * C::KSTAGE, p.k, r.x, sh, sh ? 0 : 5, BAR(B_KFULL + st));
+      const int sh = ((h * D) % 16) ? 1 : 0;         // only head dim 40 has heads that start mid-block
+      copy_kv(smem0 + C::OFF_K + st * C::KSTAGE, p.k, r.x, sh, (D == 40) ? (sh ? 0 : 5) : -1, BAR(B_KFULL + st));
     }
   } else if (warp == 2) {
     // ============================== loader: V tiles of the main jobs (+ statistic publish) ==============================
@@ -565,6 +582,8 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         const unsigned y1 = s_jobs[i + 1].y, km = JF_MAIN | JF_BIASED;
         bool same = (r.y & km) == (y1 & km);
         if (same && (r.y & km) == km) same = li == (int)((y1 >> 4) & 3);        // biased softmax jobs: same image's bias operand
+        // both jobs' Q tiles must be able to sit in shared memory at once: same unit pass, resident stages, or a ring of >= 2
+        if (same && (y1 & JF_FIRST) && !resident && C::NQ < 2) same = false;
         if (same) npair = 2;
       }
       if (is_main && biased) {
@@ -698,7 +717,7 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
             const int blk = blk0 + ks;
             const uint32_t qa = qb + (uint32_t)(blk / 4 - atom0) * kQAtom + (uint32_t)(blk % 4) * 32u;
             ptx::umma_ss(tmem_base + C::col_s(slot), ptx::make_sw128_desc(qa, 16, 1024),
-                         ptx::make_sw128_desc(kb + ks * 32, 16, 1024), idesc_qk, ks > 0);
+                         ptx::make_sw128_desc(kb + (ks / 4) * kKAtom + (ks % 4) * 32, 16, 1024), idesc_qk, ks > 0);
           }
           if (is_main && biased) {
             const uint32_t ma = qb + C::QBYTES, ca = smem0 + C::OFF_COEF + (li & 1) * kCoefTile;
@@ -1017,8 +1036,9 @@ cudaError_t launch_fused2(const XattnParams& x, const void* mpack, int64_t mpack
   } else {
     tm = tq;                                       // never dereferenced: no image is biased
   }
-  if (!tc::make_tmap_out(&to0, x.out, D, x.H, x.N, x.B, x.o_rs, x.o_bs, 32, C::C0, false) ||
-      !tc::make_tmap_out(&to1, x.out, D, x.H, x.N, x.B, x.o_rs, x.o_bs, 32, C::C1, false))
+  const int w0 = (D == 160) ? 40 : C::C0, w1 = (D == 160) ? 40 : C::C1;      // store boxes: one epilogue pass wide
+  if (!tc::make_tmap_out(&to0, x.out, D, x.H, x.N, x.B, x.o_rs, x.o_bs, 32, w0, false) ||
+      !tc::make_tmap_out(&to1, x.out, D, x.H, x.N, x.B, x.o_rs, x.o_bs, 32, w1, false))
     return cudaErrorInvalidValue;
   FxParams fp;
   fp.x = x;
