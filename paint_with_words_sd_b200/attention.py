@@ -130,13 +130,11 @@ def _rows(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
-# "fused": one launch (statistic + bias + softmax + PV, packed maps); "dense": round-1 pair of launches on the dense fp32
-# map; "auto" (default): the one-launch kernel where it is at least as fast as the pair on this hardware -- head dims 40 /
-# 80 / 160, i.e. every level of SD1.5, where the grouped-head kernel of csrc/xattn_fused2.cuh runs (N = 4096: 15.8 vs
-# 22.5 us at the cond+uncond launch, 45 vs 65 us at 16 images; N = 1024: 15.5 vs 16.6 / 27.7 vs 28.3; N = 256: 16.7 vs
-# 17.3 / 18.9 vs 22.5; profiles/r02_microbench_sd15_final.jsonl) -- and the pair at head dim 64 (SD2.1), which still has
-# only the per-head one-launch kernel (slower than the pair: profiles/r02_microbench_sd21.jsonl).  Maps that cannot be
-# packed (> 10 distinct columns) always take the dense pair.
+# "fused" / "auto" (default): ONE launch (statistic + bias + softmax + PV, packed maps; csrc/xattn_fused2.cuh) at every head
+# dim -- it matches or beats the two-launch pair on this hardware at every SD1.5 and SD2.1 shape (N = 4096 d = 40: 15.8 vs
+# 22.5 us at the cond+uncond launch, 45 vs 65 us at 16 images; N = 9216 d = 64: 21.6 vs 23.8 / 82 vs 81;
+# profiles/r02_microbench_sd15_final.jsonl, ..._sd21_final.jsonl); "dense": round 1's pair of launches on the dense fp32 map,
+# kept for maps that cannot be packed (> 10 distinct columns -- those always take it) and as a test / bench comparison.
 XATTN_IMPL = "auto"
 
 
@@ -167,7 +165,7 @@ def cross_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: in
                 wmap = wmap.unsqueeze(0)
             if wmap.shape[1] != N or wmap.shape[2] != T:
                 raise ValueError(f"weight map shape {tuple(wmap.shape)} does not match N={N}, T={T}")
-        impl = XATTN_IMPL if XATTN_IMPL != "auto" else ("fused" if D in (40, 80, 160) else "dense")
+        impl = "dense" if XATTN_IMPL == "dense" else "fused"
         if impl == "dense" and biased and wmap is None:
             impl = "fused"                          # only the packed form was given
         if biased and packed is None and impl == "fused":

@@ -189,10 +189,9 @@ int pww_xattn_fused_f16(const void* q, const void* k, const void* v, void* out, 
   cudaStream_t s = (cudaStream_t)stream;
   // image b is biased iff it has a packed map: with mpack == NULL every index is -1 (the kernel reads wmap_index)
   int chunk = pww::fx::kMaxBatch;                                  // images per launch
-  const bool grouped = (D == 40 || D == 80 || D == 160) && pww::fx::fused_variant() == 0;
-  if (grouped) {                                                   // grouped-head kernel: job table of <= 64 units per CTA
+  {                                                                // job table of <= 64 units per CTA
     const int tiles = pww::ceil_div(N, pww::fx::kBM);
-    const int hg = pww::ceil_div(H, D == 40 ? pww::fx2::Cfg2<40>::G : 1);
+    const int hg = pww::ceil_div(H, D == 40 ? pww::fx2::Cfg2<40>::G : (D == 64 ? pww::fx2::Cfg2<64>::G : 1));
     while (chunk > 1) {
       const int cb = B < chunk ? B : chunk;
       if (pww::fx2::fused2_fits(cb, hg, tiles, pww::fx::fused_grid(cb * hg * tiles))) break;
@@ -219,13 +218,10 @@ int pww_xattn_fused_f16(const void* q, const void* k, const void* v, void* out, 
     c.wmap = mpack ? (const float*)mp : nullptr;                   // non-null marks "maps present" for the kernel
     cudaError_t e = cudaErrorInvalidValue;
     switch (D) {
-      case 40: e = grouped ? pww::fx2::launch_fused2<40>(c, mp, mpack_batch_stride, Bw, ci, s)
-                           : pww::fx::launch_fused<40>(c, mp, mpack_batch_stride, Bw, ci, s); break;
-      case 64: e = pww::fx::launch_fused<64>(c, mp, mpack_batch_stride, Bw, ci, s); break;
-      case 80: e = grouped ? pww::fx2::launch_fused2<80>(c, mp, mpack_batch_stride, Bw, ci, s)
-                           : pww::fx::launch_fused<80>(c, mp, mpack_batch_stride, Bw, ci, s); break;
-      case 160: e = grouped ? pww::fx2::launch_fused2<160>(c, mp, mpack_batch_stride, Bw, ci, s)
-                            : pww::fx::launch_fused<160>(c, mp, mpack_batch_stride, Bw, ci, s); break;
+      case 40: e = pww::fx2::launch_fused2<40>(c, mp, mpack_batch_stride, Bw, ci, s); break;
+      case 64: e = pww::fx2::launch_fused2<64>(c, mp, mpack_batch_stride, Bw, ci, s); break;
+      case 80: e = pww::fx2::launch_fused2<80>(c, mp, mpack_batch_stride, Bw, ci, s); break;
+      case 160: e = pww::fx2::launch_fused2<160>(c, mp, mpack_batch_stride, Bw, ci, s); break;
     }
     if (e == cudaErrorInvalidConfiguration) return PWW_ERR_UNSUPPORTED;
     if (e != cudaSuccess) return cuda_fail(e);
@@ -340,8 +336,7 @@ int pww_debug_fwd_schedule(int B, int H, int tiles, int grid, const int* wmap_in
 }
 
 // Test infrastructure (not declared in the public header): cap the persistent grid of the fused kernel (0 = all SMs) so
-// small shapes exercise long job lists; replay the fused kernel's job lists on the host (10 int32 per job, see
-// fused_schedule_host); does CTA `cta` contribute a partial to image b's statistic?
+// small shapes exercise long job lists; does CTA `cta` contribute a partial to image b's statistic (H = head GROUPS)?
 int pww_debug_set_fused_grid(int grid) {
   pww::fx::debug_grid() = grid < 0 ? 0 : grid;
   return PWW_OK;
@@ -350,12 +345,6 @@ int pww_debug_set_fused_grid(int grid) {
 int pww_debug_set_fused_timeline(void* device_buffer, int cta) {
   pww::fx::debug_timeline() = (long long*)device_buffer;
   pww::fx::debug_timeline_cta() = cta;
-  return PWW_OK;
-}
-// Test infrastructure: 0 = grouped-head kernel at D = 40 (default), 1 = per-head one-launch kernel at every head dim (A/B timing).
-int pww_debug_set_fused_variant(int v) {
-  if (v != 0 && v != 1) return PWW_ERR_BAD_ARG;
-  pww::fx::fused_variant() = v;
   return PWW_OK;
 }
 // Host replay of the grouped-head kernel's job lists (14 int32 per job, see fused2_schedule_host).
@@ -369,10 +358,6 @@ int pww_debug_fused2_heads_per_unit(void) { return pww::fx2::Cfg2<40>::G; }
 int pww_debug_set_fused_jobs_dump(void* device_buffer) {
   pww::fx::debug_jobs_dump() = (unsigned*)device_buffer;
   return PWW_OK;
-}
-int pww_debug_fused_schedule(int B, int H, int tiles, int grid, const int* wmap_index, int* out, int max_jobs) {
-  if (!wmap_index || !out) return PWW_ERR_BAD_ARG;
-  return pww::fx::fused_schedule_host(B, H, tiles, grid, wmap_index, out, max_jobs);
 }
 int pww_debug_fused_cta_has_image(int cta, int grid, int B, int H, int tiles, const int* wmap_index, int b) {
   if (!wmap_index) return PWW_ERR_BAD_ARG;

@@ -31,15 +31,16 @@ using namespace fx;   // unit walk, helpers and constants shared with the per-he
 
 template <int D>
 struct Cfg2 {
-  static_assert(D == 40 || D == 80 || D == 160, "the grouped-head kernel is built for the SD1.5 head dims");
+  static_assert(D == 40 || D == 64 || D == 80 || D == 160, "head dims of SD1.5 (40 / 80 / 160) and SD2.x (64)");
 #ifndef PWW_FX2_G
 #define PWW_FX2_G 2
 #endif
   // heads per unit: 2 x 40 columns at head dim 40 (the unit's 80 columns sit inside 2 atoms wherever they start); one
   // head at 80 (2 atoms) and at 160 (3 atoms)
-  static constexpr int G = (D == 40) ? PWW_FX2_G : 1;
+  static constexpr int G = (D == 40) ? PWW_FX2_G : (D == 64 ? 2 : 1);     // 64: two heads = two whole atoms
   static_assert(G == 1 || G == 2 || G == 4, "heads per unit");
-  static constexpr int NAQ = (G * D > 80) ? 3 : 2;  // 64-column atoms that cover the unit's G * D columns wherever they start
+  // 64-column atoms that cover the unit's G * D columns wherever they start (head dim 64: units are atom aligned)
+  static constexpr int NAQ = (D == 64) ? G : ((G * D > 80) ? 3 : 2);
   static constexpr int NA = (D + 63) / 64;          // 64-column atoms of a head's K / V tile
   static constexpr int DP = (D + 15) / 16 * 16;
   static constexpr int KSTEPS = DP / 16;            // 16-column blocks per head (at 40: 3, the head starts 0 or 8 columns into its first block)
@@ -52,8 +53,8 @@ struct Cfg2 {
   __host__ __device__ static constexpr uint32_t col_o(int os) { return (uint32_t)NS * 80u + (uint32_t)os * O_STRIDE; }
   static_assert(NS * 80 + NO * DPV <= 512, "TMEM budget");
   static constexpr int NQ = (D == 160) ? 1 : 2;     // Q ring: unit passes in flight (or resident units)
-  static constexpr int NK = (D == 40) ? 3 : 2;      // K ring: jobs in flight
-  static constexpr int NV = (D == 40) ? 3 : (D == 80 ? 2 : 1);  // V ring: main jobs in flight
+  static constexpr int NK = (D <= 64) ? 3 : 2;      // K ring: jobs in flight
+  static constexpr int NV = (D <= 64) ? 3 : (D == 80 ? 2 : 1);  // V ring: main jobs in flight
   static constexpr uint32_t QBYTES = NAQ * kQAtom;
   static constexpr uint32_t QSTAGE = QBYTES + kMAtom;           // Q atoms | packed-map atom of the row tile
   static constexpr uint32_t KSTAGE = NA * kKAtom, VSTAGE = NA * kKAtom;

@@ -1,7 +1,10 @@
-"""CPU checks of the grouped-head one-launch kernel's job lists (csrc/xattn_fused2.cuh: Fx2Jobs over FxWalk with head
-groups), replayed on the host by the library itself.  On top of the per-head kernel's invariants (tests/
-test_fused_schedule.py): the jobs of a unit pass are consecutive, flagged first ... last, share one `up`; `up` counts the
-unit passes of a CTA in order (the Q ring index); `ul` is the unit's position in the CTA's range (the resident stage)."""
+"""CPU checks of the one-launch kernel's job lists (csrc/xattn_fused2.cuh: Fx2Jobs over FxWalk with head groups), replayed
+on the host by the library itself (the same code the kernel's host-replay test compares the device-built tables with).
+What must hold: every (image, head, row tile) is a softmax job exactly once; every unit of an image with a weight map is
+a statistic job exactly once, before any softmax job of its CTA; the unbiased softmax jobs of a CTA precede its biased
+ones (they overlap the grid barrier); the jobs of a unit pass are consecutive, flagged first ... last, share one `up`;
+`up` counts the unit passes of a CTA in order (the Q ring index); `ul` is the unit's position in the CTA's range (the
+resident stage); the set of CTAs the barrier of image b waits for is exactly the set that publishes a partial for b."""
 import ctypes
 import itertools
 
@@ -24,6 +27,15 @@ def _jobs(B, H, tiles, grid, widx, g=G):
     n = L.pww_debug_fused2_schedule(B, H, g, tiles, grid, w.ctypes.data, out.ctypes.data, cap)
     assert n >= 0
     return out[:n]
+
+
+def _has_image(cta, grid, B, H, tiles, widx, b):
+    """Does CTA `cta` publish a statistic partial for image b?  (the library's membership test, head GROUPS as heads)"""
+    L = _native.lib()
+    L.pww_debug_fused_cta_has_image.restype = ctypes.c_int
+    L.pww_debug_fused_cta_has_image.argtypes = [ctypes.c_int] * 5 + [ctypes.c_void_p, ctypes.c_int]
+    w = np.asarray(widx, dtype=np.int32)
+    return L.pww_debug_fused_cta_has_image(cta, grid, B, (H + G - 1) // G, tiles, w.ctypes.data, b)
 
 
 CASES = [
@@ -81,6 +93,13 @@ def test_job_lists(B, H, tiles, grid, widx):
             assert 0 <= r[0, 11] < u1 - u0
         # every unit of the range is visited: distinct (ul) values == number of units
         assert set(rows[:, 11].tolist()) == set(range(u1 - u0))
+    # grid barrier membership: the CTAs image b's waiters expect == the CTAs that run a statistic job of image b
+    for b in range(B):
+        if widx[b] < 0:
+            continue
+        publishers = set(stat[stat[:, 4] == b][:, 0].tolist())
+        expected = {c for c in range(grid) if _has_image(c, grid, B, H, tiles, widx, b)}
+        assert publishers == expected, (b, sorted(publishers ^ expected))
 
 
 def test_the_workload_launch_is_resident():

@@ -281,10 +281,8 @@ def test_fused_all_biased_and_all_unbiased_batches():
 
 
 def test_default_dispatch_per_head_dim():
-    """The shim's default picks the one-launch kernel at the SD1.5 head dims (40 / 80 / 160: the grouped-head kernel) and
-    the two-launch pair at 64 (measured: the grouped-head kernel matches or beats the pair, the per-head one-launch
-    kernel does not)."""
-    for (N, H, D, launches) in ((1024, 8, 40, 1), (256, 8, 80, 1), (64, 8, 160, 1), (256, 5, 64, 2)):
+    """The shim's default is the one-launch kernel at every head dim."""
+    for (N, H, D, launches) in ((1024, 8, 40, 1), (256, 8, 80, 1), (64, 8, 160, 1), (256, 5, 64, 1)):
         q, k, v, w = _inputs(1, N, H, D, 77, seed=N + D)
         before = _native.launch_count
         got, st = _run(q, k, v, H, D ** -0.5, w, 0.6, "max", impl="auto")
