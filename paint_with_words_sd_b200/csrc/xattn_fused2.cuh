@@ -35,6 +35,9 @@ struct Cfg2 {
 #ifndef PWW_FX2_G
 #define PWW_FX2_G 2
 #endif
+#ifndef PWW_FX2_XTOKEN
+#define PWW_FX2_XTOKEN 0
+#endif
   // heads per unit: 2 x 40 columns at head dim 40 (the unit's 80 columns sit inside 2 atoms wherever they start); one
   // head at 80 (2 atoms) and at 160 (3 atoms)
   static constexpr int G = (D == 40) ? PWW_FX2_G : (D == 64 ? 2 : 1);     // 64: two heads = two whole atoms
@@ -158,6 +161,7 @@ struct Fx2Jobs {
 //   s_jobs[i].x = b | h << 8 | tile << 16          s_jobs[i].y = flags, see the JF_* masks
 constexpr int kMaxUnits = 64;        // units per CTA (host-checked: the C ABI splits larger batches)
 constexpr int kMaxJobs = 512;        // kMaxUnits * G heads * 2 passes
+constexpr bool kXToken = PWW_FX2_XTOKEN != 0;   // experiment: softmax groups take turns on the MUFU (see the softmax role)
 constexpr uint32_t JF_MAIN = 1u, JF_BIASED = 2u, JF_FIRST = 4u, JF_LAST = 8u;   // | li << 4 (2 bits) | ul << 8 (8 bits)
 
 // Order-preserving map float -> unsigned (0 is below every real number: a zero-filled workspace reads as -infinity).
@@ -207,7 +211,7 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   const uint32_t bar0 = smem0 + C::OFF_BAR;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   constexpr int B_QFULL = 0, B_QEMPTY = 2, B_KFULL = 4, B_KEMPTY = 7, B_VFULL = 10, B_VEMPTY = 13, B_SREADY = 16,
-                B_SFREE = 20, B_PREADY = 24, B_PVDONE = 28, B_OFREE = 32, B_COEF = 36, B_TMEMPTR = 38, B_STATS = 39;
+                B_SFREE = 20, B_PREADY = 24, B_PVDONE = 28, B_OFREE = 32, B_COEF = 36, B_TMEMPTR = 38, B_STATS = 39, B_XDONE = 40;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = TT ? TT : p.T;
   int u0, u1;
@@ -409,6 +413,10 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     ptx::mbar_init(BAR(B_COEF + 0), 1);
     ptx::mbar_init(BAR(B_COEF + 1), 1);
     ptx::mbar_init(BAR(B_STATS), 16);             // every softmax warp has written its statistic partials
+    if constexpr (kXToken) {
+      ptx::mbar_init(BAR(B_XDONE + 0), 8);        // a softmax group has issued its job's exponentials
+      ptx::mbar_init(BAR(B_XDONE + 1), 8);
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -492,8 +500,10 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       //      8 columns into its first 16-column block); the chunk column the shift leaves free is zeroed ----
       const int st = i % C::NK;
       ptx::mbar_wait(BAR(B_KEMPTY + st), (uint32_t)(((i / C::NK) & 1) ^ 1));
+      if (lane == 0) FX_TL(16, i);
       const int sh = ((h * D) % 16) ? 1 : 0;         // only head dim 40 has heads that start mid-block
       copy_kv(smem0 + C::OFF_K + st * C::KSTAGE, p.k, r.x, sh, (D == 40) ? (sh ? 0 : 5) : -1, BAR(B_KFULL + st));
+      if (lane == 0) FX_TL(17, i);
     }
   } else if (warp == 2) {
     // ============================== loader: V tiles of the main jobs (+ statistic publish) ==============================
@@ -534,7 +544,9 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         publish();
       }
       ptx::mbar_wait(BAR(B_VEMPTY + st), (uint32_t)(((m / C::NV) & 1) ^ 1));
+      if (lane == 0) FX_TL(18, i);
       copy_kv(smem0 + C::OFF_V + st * C::VSTAGE, p.v, s_jobs[i].x, 0, -1, BAR(B_VFULL + st));
+      if (lane == 0) FX_TL(19, i);
     }
     if (ns > 0 && njobs - ns <= C::NV) {           // fewer main jobs than ring stages: not published inside the loop
       ptx::mbar_wait(BAR(B_STATS), 0);
@@ -689,6 +701,11 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         qst_t[t] = qst;
         // the unit's Q tile (resident stages complete exactly one phase; ring stages one phase per unit pass): first job only
         if (rt.y & JF_FIRST) ptx::mbar_wait(BAR(B_QFULL + qst), resident ? 0u : (uint32_t)((up / C::NQ) & 1));
+        if (lane == 0) FX_TL(1, it);
+        if constexpr (kTimeline) {                   // timeline builds only: the K wait on its own, so that it gets a stamp
+          ptx::mbar_wait(BAR(B_KFULL + kst), (uint32_t)((it / C::NK) & 1));
+          if (lane == 0) FX_TL(7, it);
+        }
         // this job's K tile, and the score slot: the previous job on it (it - NS) must be done with it
         if (it >= C::NS) {
           const int prev = it - C::NS;
@@ -742,6 +759,10 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       const int m = i - ns;
       const int st = m % C::NV, slot = i % C::NS, os = i % C::NO;
       // the V tile, the group's P (written over S in tensor memory) and the output accumulator of 4 jobs ago
+      if constexpr (kTimeline) {                     // timeline builds only: the V wait on its own, so that it gets a stamp
+        ptx::mbar_wait(BAR(B_VFULL + st), (uint32_t)((m / C::NV) & 1));
+        if (lane == 0) FX_TL(20, i);
+      }
       if (m >= C::NO)
         ptx::mbar_wait3(BAR(B_VFULL + st), (uint32_t)((m / C::NV) & 1), BAR(B_PREADY + slot), (uint32_t)((m / C::NS) & 1),
                         BAR(B_OFREE + os), (uint32_t)(((m / C::NO) - 1) & 1));
@@ -856,6 +877,7 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     int pend_slot = 0, pend_os = 0, pend_ph = 0, pend_n0 = 0, pend_b = 0, pend_h = 0, pend_xb = 0;
     float pend_sum = 0.f;
     int xb = 0;                                    // exchange buffer parity of this group's next job
+    const bool xtok = njobs - ns >= 8;             // kXToken builds: take turns on the MUFU when the job list is long
 
     auto epilogue = [&]() {                        // O (fp32, TMEM) -> * 1/rowsum -> fp16 -> staging -> TMA store
       ptx::mbar_wait(BAR(B_PVDONE + pend_slot), (uint32_t)pend_ph);
@@ -938,6 +960,12 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         ptx::named_bar_sync(pair_bar, 64);
         mx = fmaxf(mx, xm[(c ^ 1) * 128 + row]);
         const float nm = -mx * sl2;
+        if constexpr (kXToken) {
+          // One group in its exponential phase at a time, in job order (long job lists only).  Both groups get their S
+          // together (the issuer works in pairs), and two groups' exponentials at once share the 16-lane MUFU: each takes
+          // twice as long and then both sit in their epilogues with the unit idle.
+          if (xtok && i - 1 >= ns) ptx::mbar_wait(BAR(B_XDONE + (g ^ 1)), (uint32_t)(((i - 1 - (ns + ((ns & 1) ^ g ^ 1))) >> 1) & 1));
+        }
         // p_j = 2^(s_j*sl2 - mx*sl2), UNNORMALISED, packed to fp16; O is scaled by 1/rowsum in the epilogue (fp32)
         float a0 = 0.f, a1 = 0.f;
         uint32_t pk[20];
@@ -951,6 +979,7 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
             a0 += f.x; a1 += f.y;
           }
         }
+        if constexpr (kXToken) { if (xtok) warp_arrive(BAR(B_XDONE + g)); }
         if constexpr (!C::ONES) xsum[((g * 2 + xb) * 2 + c) * 128 + row] = a0 + a1;
         // P (packed fp16) over the S columns it came from: this half owns P columns [20c, 20c + 20)
         ptx::tmem_st16_u32(ts + c * 20, pk);

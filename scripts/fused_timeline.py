@@ -39,7 +39,12 @@ for _ in range(20):          # warm clocks
 torch.cuda.synchronize()
 TAGS, ITS = 24, 64
 buf = torch.zeros(TAGS * ITS, dtype=torch.int64, device=dev)
-flush.fill_(1)
+# L2 of the previous launches' Q / K / V is evicted by READING a large buffer (clean lines: a fill would leave the L2 full of
+# dirty lines whose write-back the timed launch then pays for)
+if os.environ.get("PWW_TL_FLUSH", "read") == "read":
+    flush.view(torch.int32).sum().item()
+else:
+    flush.fill_(1)
 torch.cuda.synchronize()
 assert L.pww_debug_set_fused_timeline(buf.data_ptr(), cta) == 0
 A.cross_attention(q, k, v, H, D ** -0.5, None, idx, _native.PWW_STAT_MAX, gs, packed=pk if biased else None)
@@ -52,8 +57,10 @@ print(f"B={B} biased={biased} cta={cta} N={N} H={H} D={D}; cycles since the post
 print(f"kernel entry {f(21, 0)}; job table built {f(22, 0)}; TMEM allocated {f(23, 0)} (cycles relative to the post-prologue sync)")
 print(f"first Q load about to issue {f(15, 1)} {f(15, 2)}")
 print(f"grid barrier: start {f(10, 0)} end {f(11, 0)}; publish {f(12, 0)}; softmax groups done {f(14, 0)} {f(14, 1)}; kernel end {f(15, 0)}")
-print(" i | tma_issued  qfull  slot_free  s_issued | sready  math_done(pready/sfree)  epi_done | vfull  pready_seen  pv_issued")
+print("S issuer: q_issued(TMA) | q_ready k_ready all_ready s_issued || softmax: s_seen p_ready epi_done || PV: v_ready all_ready pv_issued "
+      "|| loaders: k_stage_free k_copied v_stage_free v_copied")
+g = lambda tag, it: f"{f(tag, it):7d}" if tab[tag, it] > 0 else "      ."   # noqa: E731
 for it in range(ITS):
     if tab[0, it] > 0 or tab[3, it] > 0 or tab[16, it] > 0:
-        print(f"{it:2d} | {f(0, it):7d} {f(1, it):7d} {f(2, it):7d} {f(3, it):7d} | {f(4, it):7d} {f(5, it):7d} {f(6, it):7d} | "
-              f"{f(7, it):7d} {f(8, it):7d} {f(9, it):7d}")
+        print(f"{it:2d} | {g(0, it)} | {g(1, it)} {g(7, it)} {g(2, it)} {g(3, it)} || {g(4, it)} {g(5, it)} {g(6, it)} || "
+              f"{g(20, it)} {g(8, it)} {g(9, it)} || {g(16, it)} {g(17, it)} {g(18, it)} {g(19, it)}")

@@ -1,5 +1,5 @@
 """Kernel-only timing of the PwW cross-attention op (the roofline leg of bench.py, standalone):
-python scripts/xattn_microbench.py [sd21] [dense]   -- `dense` also times the round-1 two-launch path on the same inputs."""
+python scripts/xattn_microbench.py [sd21] [dense] [quick]   -- `dense` also times the round-1 two-launch path on the same inputs."""
 import json
 import os
 import sys
@@ -15,6 +15,8 @@ shapes = [(4096, 8, 40), (1024, 8, 80), (256, 8, 160), (64, 8, 160)]
 if "sd21" in sys.argv[1:]:
     shapes = [(9216, 5, 64), (2304, 10, 64), (576, 20, 64), (144, 20, 64)]
 dense = "dense" in sys.argv[1:]
+if "quick" in sys.argv[1:]:
+    shapes = shapes[:1]
 for (N, H, D) in shapes:
     for (B, biased) in [(2, 1), (16, 8)]:
         r = bench.xattn_roofline(dev, B=B, biased=biased, N=N, H=H, D=D, iters=32 if B > 2 else 64, dense_pair=dense)
