@@ -265,6 +265,29 @@ def test_fused_long_job_lists(N, H, D, B, grid, stat):
         assert torch.equal(full, got) and torch.equal(st_full, st)
 
 
+def test_fused_std_long_job_lists_repeat_bit_identically():
+    """compute-sanitizer racecheck reports write-after-write hazards on the V ring for the std statistic at head dim 40
+    (profiles/r02_sanitizer_all.txt; max and the other head dims are clean).  The ring's release is a tcgen05.commit
+    arrival on an mbarrier, which the tool does not model; a real overwrite of a V tile that is still being read would make
+    the output depend on timing.  40 launches of that configuration must agree bit for bit (fixed grid: the std partials
+    are summed in CTA order) and with the oracle."""
+    N, H, D, T, B = 1024, 8, 40, 77, 4
+    q, k, v, w = _inputs(B, N, H, D, T, seed=4242)
+    idx = torch.tensor([0, -1, 1, -1], dtype=torch.int32)
+    g = 0.4 * math.log(1 + 5.0)
+    w_eff = torch.stack([w[0], torch.zeros(N, T), w[1], torch.zeros(N, T)])
+    ref32, _ = _oracle(q, k, v, H, D ** -0.5, w_eff, g, "std", emulate=False)
+    _set_fused_grid(6)
+    try:
+        first, st0 = _run(q, k, v, H, D ** -0.5, w[:2].contiguous(), g, "std", idx)
+        assert (first - ref32).abs().max().item() <= 2e-3 * ref32.abs().max().item()
+        for _ in range(39):
+            again, st = _run(q, k, v, H, D ** -0.5, w[:2].contiguous(), g, "std", idx)
+            assert torch.equal(again, first) and torch.equal(st, st0)
+    finally:
+        _set_fused_grid(0)
+
+
 def test_fused_all_biased_and_all_unbiased_batches():
     """Batches without a partner image of the other kind (solo groups of the unit order)."""
     N, H, D, T = 1024, 8, 40, 77
