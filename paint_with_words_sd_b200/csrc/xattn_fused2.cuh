@@ -20,6 +20,7 @@
 // per ring stage) as 16-byte cp.async copies that arrive on the stage's mbarrier -- no staging registers, a whole ring of
 // tiles in flight.
 #pragma once
+#include <type_traits>
 #include "ptx_sm100.cuh"
 #include "pww_common.cuh"
 #include "xattn_tc.cuh"   // make_tmap, make_tmap_out, encode_fn, num_sms, tc_error_buf
@@ -38,6 +39,12 @@ struct Cfg2 {
 #ifndef PWW_FX2_XTOKEN
 #define PWW_FX2_XTOKEN 0
 #endif
+#ifndef PWW_FX2_NQ40
+#define PWW_FX2_NQ40 2
+#endif
+#ifndef PWW_FX2_KVCOAL
+#define PWW_FX2_KVCOAL 2
+#endif
   // heads per unit: 2 x 40 columns at head dim 40 (the unit's 80 columns sit inside 2 atoms wherever they start); one
   // head at 80 (2 atoms) and at 160 (3 atoms)
   static constexpr int G = (D == 40) ? PWW_FX2_G : (D == 64 ? 2 : 1);     // 64: two heads = two whole atoms
@@ -55,7 +62,7 @@ struct Cfg2 {
   __host__ __device__ static constexpr uint32_t col_s(int slot) { return (uint32_t)slot * 80u; }
   __host__ __device__ static constexpr uint32_t col_o(int os) { return (uint32_t)NS * 80u + (uint32_t)os * O_STRIDE; }
   static_assert(NS * 80 + NO * DPV <= 512, "TMEM budget");
-  static constexpr int NQ = (D == 160) ? 1 : 2;     // Q ring: unit passes in flight (or resident units)
+  static constexpr int NQ = (D == 160) ? 1 : (D == 40 ? PWW_FX2_NQ40 : 2);     // Q ring: unit passes in flight (or resident units)
   static constexpr int NK = (D <= 64) ? 3 : 2;      // K ring: jobs in flight
   static constexpr int NV = (D <= 64) ? 3 : (D == 80 ? 2 : 1);  // V ring: main jobs in flight
   static constexpr uint32_t QBYTES = NAQ * kQAtom;
@@ -72,7 +79,9 @@ struct Cfg2 {
   static constexpr uint32_t OFF_COEF = OFF_V + NV * VSTAGE;     // 2 B-operand tiles [80 x 32 fp16], 64-byte-swizzled rows
   static constexpr uint32_t OFF_STG = OFF_COEF + 2 * kCoefTile;
   static constexpr uint32_t OFF_XCHG = OFF_STG + 16 * STG_WARP; // [group][buf][half][128] fp32 row maxima, then row sums
-  static constexpr uint32_t OFF_BAR = OFF_XCHG + 2 * 2 * 2 * 128 * 4 * 2;
+  // row maxima always; row sums only where they do not ride on the P.V UMMA
+  static constexpr uint32_t XCHG_BYTES = 2 * 2 * 2 * 128 * 4 * ((ONES && NQ > 2) ? 1 : 2);
+  static constexpr uint32_t OFF_BAR = OFF_XCHG + XCHG_BYTES;
   static constexpr uint32_t SMEM = OFF_BAR + 512 + 1024;        // + alignment slack
   static_assert(SMEM + 7680 <= 232448, "shared memory budget (dynamic + ~7.3 KB of static tables incl. the 4 KB job table)");
   static_assert(16 * STG_WARP >= 64 * 16, "the job-table scratch (kMaxUnits x 16 bytes) lives in the staging area");
@@ -161,6 +170,11 @@ struct Fx2Jobs {
 //   s_jobs[i].x = b | h << 8 | tile << 16          s_jobs[i].y = flags, see the JF_* masks
 constexpr int kMaxUnits = 64;        // units per CTA (host-checked: the C ABI splits larger batches)
 constexpr int kMaxJobs = 512;        // kMaxUnits * G heads * 2 passes
+// K / V tile copies with consecutive lanes along a row's chunks: 0 = never, 1 = always, 2 = every head dim but 40.  Measured
+// (profiles/r02_kvcoal_*): 4-12 % faster launches at head dims 64 / 80 / 160; at 40 the 5- and 6-chunk rows make the index
+// arithmetic dearer than the wavefronts it saves (B = 16: +2.8 %), so that head dim keeps one lane per row.
+template <int D>
+constexpr bool kKvCoalesced = PWW_FX2_KVCOAL == 1 || (PWW_FX2_KVCOAL == 2 && D != 40);
 constexpr bool kXToken = PWW_FX2_XTOKEN != 0;   // experiment: softmax groups take turns on the MUFU (see the softmax role)
 constexpr uint32_t JF_MAIN = 1u, JF_BIASED = 2u, JF_FIRST = 4u, JF_LAST = 8u;   // | li << 4 (2 bits) | ul << 8 (8 bits)
 
@@ -210,8 +224,11 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   unsigned char* smem_gen = smem_raw + (smem0 - ptx::smem_u32(smem_raw));
   const uint32_t bar0 = smem0 + C::OFF_BAR;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  constexpr int B_QFULL = 0, B_QEMPTY = 2, B_KFULL = 4, B_KEMPTY = 7, B_VFULL = 10, B_VEMPTY = 13, B_SREADY = 16,
-                B_SFREE = 20, B_PREADY = 24, B_PVDONE = 28, B_OFREE = 32, B_COEF = 36, B_TMEMPTR = 38, B_STATS = 39, B_XDONE = 40;
+  constexpr int NQB = C::NQ > 2 ? C::NQ : 2, QO = 2 * NQB - 4;       // barrier slots of the Q ring; everything after shifts
+  constexpr int B_QFULL = 0, B_QEMPTY = NQB, B_KFULL = 4 + QO, B_KEMPTY = 7 + QO, B_VFULL = 10 + QO, B_VEMPTY = 13 + QO,
+                B_SREADY = 16 + QO, B_SFREE = 20 + QO, B_PREADY = 24 + QO, B_PVDONE = 28 + QO, B_OFREE = 32 + QO,
+                B_COEF = 36 + QO, B_TMEMPTR = 38 + QO, B_STATS = 39 + QO, B_XDONE = 40 + QO;
+  static_assert(C::NQ <= 3 && (B_XDONE + 2) * 8 <= 512, "barrier table");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = TT ? TT : p.T;
   int u0, u1;
@@ -449,6 +466,26 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   auto copy_kv = [&](uint32_t tile, const __half* base, unsigned x, int shift, int zc, uint32_t bar) {
     const int b = x & 0xff, h = (x >> 8) & 0xff;
     const __half* src = base + (fp.k_batched ? (int64_t)b * p.k_bs : 0) + h * D;
+    if constexpr (kKvCoalesced<D>) {
+      // Consecutive lanes take consecutive 16-byte chunks of a row (then the next row): one warp instruction reads a few
+      // whole rows, i.e. a handful of LSU wavefronts, instead of one chunk of 32 different rows = 32 wavefronts.
+      auto rows = [&](auto cpr_tag) {
+        constexpr int CPR = decltype(cpr_tag)::value;      // chunk columns written per row
+        const int total = T * CPR;
+#pragma unroll 4
+        for (int idx = lane; idx < total; idx += 32) {
+          const int t = idx / CPR, c = idx - t * CPR;      // destination chunk column c of row t
+          const bool zero = c == zc;
+          const int ch = zero ? 0 : c - shift;             // source chunk of the head's row
+          const uint4* srow = reinterpret_cast<const uint4*>(src + (int64_t)t * p.k_rs);
+          cp_async16(tile + t * 128 + (c >> 3) * kKAtom + (((c & 7) ^ (t & 7)) << 4), srow + ch, zero ? 0u : 16u);
+        }
+      };
+      if (zc >= 0) rows(std::integral_constant<int, D / 8 + 1>{});   // K at head dim 40: the data chunks and the zeroed one
+      else rows(std::integral_constant<int, D / 8>{});
+      cp_async_arrive(bar);
+      return;
+    }
 #pragma unroll
     for (int jj = 0; jj < (kTP + 31) / 32; ++jj) {       // a lane owns whole rows: one address computation per row
       const int t = lane + 32 * jj;
