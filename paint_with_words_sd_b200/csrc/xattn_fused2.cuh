@@ -36,12 +36,6 @@ struct Cfg2 {
 #ifndef PWW_FX2_G
 #define PWW_FX2_G 2
 #endif
-#ifndef PWW_FX2_XTOKEN
-#define PWW_FX2_XTOKEN 0
-#endif
-#ifndef PWW_FX2_NQ40
-#define PWW_FX2_NQ40 2
-#endif
 #ifndef PWW_FX2_KVCOAL
 #define PWW_FX2_KVCOAL 2
 #endif
@@ -62,7 +56,7 @@ struct Cfg2 {
   __host__ __device__ static constexpr uint32_t col_s(int slot) { return (uint32_t)slot * 80u; }
   __host__ __device__ static constexpr uint32_t col_o(int os) { return (uint32_t)NS * 80u + (uint32_t)os * O_STRIDE; }
   static_assert(NS * 80 + NO * DPV <= 512, "TMEM budget");
-  static constexpr int NQ = (D == 160) ? 1 : (D == 40 ? PWW_FX2_NQ40 : 2);     // Q ring: unit passes in flight (or resident units)
+  static constexpr int NQ = (D == 160) ? 1 : 2;     // Q ring: unit passes in flight (or resident units)
   static constexpr int NK = (D <= 64) ? 3 : 2;      // K ring: jobs in flight
   static constexpr int NV = (D <= 64) ? 3 : (D == 80 ? 2 : 1);  // V ring: main jobs in flight
   static constexpr uint32_t QBYTES = NAQ * kQAtom;
@@ -79,9 +73,7 @@ struct Cfg2 {
   static constexpr uint32_t OFF_COEF = OFF_V + NV * VSTAGE;     // 2 B-operand tiles [80 x 32 fp16], 64-byte-swizzled rows
   static constexpr uint32_t OFF_STG = OFF_COEF + 2 * kCoefTile;
   static constexpr uint32_t OFF_XCHG = OFF_STG + 16 * STG_WARP; // [group][buf][half][128] fp32 row maxima, then row sums
-  // row maxima always; row sums only where they do not ride on the P.V UMMA
-  static constexpr uint32_t XCHG_BYTES = 2 * 2 * 2 * 128 * 4 * ((ONES && NQ > 2) ? 1 : 2);
-  static constexpr uint32_t OFF_BAR = OFF_XCHG + XCHG_BYTES;
+  static constexpr uint32_t OFF_BAR = OFF_XCHG + 2 * 2 * 2 * 128 * 4 * 2;
   static constexpr uint32_t SMEM = OFF_BAR + 512 + 1024;        // + alignment slack
   static_assert(SMEM + 7680 <= 232448, "shared memory budget (dynamic + ~7.3 KB of static tables incl. the 4 KB job table)");
   static_assert(16 * STG_WARP >= 64 * 16, "the job-table scratch (kMaxUnits x 16 bytes) lives in the staging area");
@@ -175,7 +167,6 @@ constexpr int kMaxJobs = 512;        // kMaxUnits * G heads * 2 passes
 // arithmetic dearer than the wavefronts it saves (B = 16: +2.8 %), so that head dim keeps one lane per row.
 template <int D>
 constexpr bool kKvCoalesced = PWW_FX2_KVCOAL == 1 || (PWW_FX2_KVCOAL == 2 && D != 40);
-constexpr bool kXToken = PWW_FX2_XTOKEN != 0;   // experiment: softmax groups take turns on the MUFU (see the softmax role)
 constexpr uint32_t JF_MAIN = 1u, JF_BIASED = 2u, JF_FIRST = 4u, JF_LAST = 8u;   // | li << 4 (2 bits) | ul << 8 (8 bits)
 
 // Order-preserving map float -> unsigned (0 is below every real number: a zero-filled workspace reads as -infinity).
@@ -224,11 +215,8 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   unsigned char* smem_gen = smem_raw + (smem0 - ptx::smem_u32(smem_raw));
   const uint32_t bar0 = smem0 + C::OFF_BAR;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  constexpr int NQB = C::NQ > 2 ? C::NQ : 2, QO = 2 * NQB - 4;       // barrier slots of the Q ring; everything after shifts
-  constexpr int B_QFULL = 0, B_QEMPTY = NQB, B_KFULL = 4 + QO, B_KEMPTY = 7 + QO, B_VFULL = 10 + QO, B_VEMPTY = 13 + QO,
-                B_SREADY = 16 + QO, B_SFREE = 20 + QO, B_PREADY = 24 + QO, B_PVDONE = 28 + QO, B_OFREE = 32 + QO,
-                B_COEF = 36 + QO, B_TMEMPTR = 38 + QO, B_STATS = 39 + QO, B_XDONE = 40 + QO;
-  static_assert(C::NQ <= 3 && (B_XDONE + 2) * 8 <= 512, "barrier table");
+  constexpr int B_QFULL = 0, B_QEMPTY = 2, B_KFULL = 4, B_KEMPTY = 7, B_VFULL = 10, B_VEMPTY = 13, B_SREADY = 16,
+                B_SFREE = 20, B_PREADY = 24, B_PVDONE = 28, B_OFREE = 32, B_COEF = 36, B_TMEMPTR = 38, B_STATS = 39;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = TT ? TT : p.T;
   int u0, u1;
@@ -430,10 +418,6 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     ptx::mbar_init(BAR(B_COEF + 0), 1);
     ptx::mbar_init(BAR(B_COEF + 1), 1);
     ptx::mbar_init(BAR(B_STATS), 16);             // every softmax warp has written its statistic partials
-    if constexpr (kXToken) {
-      ptx::mbar_init(BAR(B_XDONE + 0), 8);        // a softmax group has issued its job's exponentials
-      ptx::mbar_init(BAR(B_XDONE + 1), 8);
-    }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -914,7 +898,6 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     int pend_slot = 0, pend_os = 0, pend_ph = 0, pend_n0 = 0, pend_b = 0, pend_h = 0, pend_xb = 0;
     float pend_sum = 0.f;
     int xb = 0;                                    // exchange buffer parity of this group's next job
-    const bool xtok = njobs - ns >= 8;             // kXToken builds: take turns on the MUFU when the job list is long
 
     auto epilogue = [&]() {                        // O (fp32, TMEM) -> * 1/rowsum -> fp16 -> staging -> TMA store
       ptx::mbar_wait(BAR(B_PVDONE + pend_slot), (uint32_t)pend_ph);
@@ -997,12 +980,6 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         ptx::named_bar_sync(pair_bar, 64);
         mx = fmaxf(mx, xm[(c ^ 1) * 128 + row]);
         const float nm = -mx * sl2;
-        if constexpr (kXToken) {
-          // One group in its exponential phase at a time, in job order (long job lists only).  Both groups get their S
-          // together (the issuer works in pairs), and two groups' exponentials at once share the 16-lane MUFU: each takes
-          // twice as long and then both sit in their epilogues with the unit idle.
-          if (xtok && i - 1 >= ns) ptx::mbar_wait(BAR(B_XDONE + (g ^ 1)), (uint32_t)(((i - 1 - (ns + ((ns & 1) ^ g ^ 1))) >> 1) & 1));
-        }
         // p_j = 2^(s_j*sl2 - mx*sl2), UNNORMALISED, packed to fp16; O is scaled by 1/rowsum in the epilogue (fp32)
         float a0 = 0.f, a1 = 0.f;
         uint32_t pk[20];
@@ -1016,7 +993,6 @@ xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
             a0 += f.x; a1 += f.y;
           }
         }
-        if constexpr (kXToken) { if (xtok) warp_arrive(BAR(B_XDONE + g)); }
         if constexpr (!C::ONES) xsum[((g * 2 + xb) * 2 + c) * 128 + row] = a0 + a1;
         // P (packed fp16) over the S columns it came from: this half owns P columns [20c, 20c + 20)
         ptx::tmem_st16_u32(ts + c * 20, pk);
